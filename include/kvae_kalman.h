@@ -1,0 +1,140 @@
+/* kvae_kalman.h — C ABI of the B200-native Kalman filter / RTS smoother / ELBO / adjoint.
+ *
+ * This is the drop-in boundary for the hot path of rodrigo-paganini/kalman-vae.  The reference has
+ * no FFI of its own (it is pure PyTorch); every entry point below names the reference interface
+ * whose arithmetic it replaces (paths relative to the reference checkout):
+ *
+ *   kvae_kf_filter_smooth_fwd  <- KalmanFilter.filter   kvae/kalman/kalman_filter.py:107-201
+ *                                 KalmanFilter.smooth   kvae/kalman/kalman_filter.py:240-279
+ *                                 (filter_step :31-104, smooth_step :204-237) including the mixing
+ *                                 DynamicsParameter.compute_step      kvae/kalman/dyn_param.py:58-60
+ *                                 SwitchingDynamicsParameter.compute_batch
+ *                                                                     kvae/kalman/switch_dyn_param.py:82-86
+ *   kvae_kf_elbo_fwd           <- KalmanFilter.elbo     kvae/kalman/kalman_filter.py:305-401
+ *                                 (_safe_cholesky :282-302, first attempt: jitter*I added)
+ *   kvae_kf_bwd                <- loss.backward() through all of the above
+ *                                 (kvae/train/train.py:53; the reference relies on autograd)
+ *
+ * Conventions
+ *   - all tensors are contiguous fp32 DEVICE buffers in the reference's batch-major layouts
+ *     ([B,T,...], kalman_filter.py:193-201); base pointers must be 16-byte aligned.
+ *     Means are [B,T,n] (the reference's trailing singleton dimension does not change the layout).
+ *   - nothing is allocated, no host synchronisation happens; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) of device `device`
+ *     (-1 = current device).  Every entry point is re-entrant (autograd calls backward from
+ *     another thread than forward).
+ *   - return value: 0 ok; <0 invalid argument / unsupported shape (see kvae_last_error());
+ *     >0 a cudaError_t raised by the launch.
+ *   - `info` is a device int32 the kernels set to non-zero when a factorisation met a
+ *     non-positive pivot (the reference would raise torch.linalg.LinAlgError or, in
+ *     _safe_cholesky, retry with 10x jitter); the caller zeroes it and decides when to read it.
+ */
+#ifndef KVAE_KALMAN_H
+#define KVAE_KALMAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVAE_ABI_VERSION 1
+
+typedef struct kvae_dims {
+  int32_t B;          /* sequences in this call (the per-rank shard)               */
+  int32_t T;          /* time steps                                               */
+  int32_t n;          /* z_dim  (state)                                           */
+  int32_t p;          /* a_dim  (observation)                                     */
+  int32_t m;          /* u_dim  (control)                                         */
+  int32_t K;          /* number of base matrices mixed by alpha                   */
+  int32_t q_per_mode; /* 1: Q is [K,n,n], Q_t = sum_k alpha_k Q_k (switching)     */
+                      /* 0: Q is [n,n] fixed (lstm, KalmanFilter.Q buffer)        */
+  int32_t c_shared;   /* 1: C_t = C[0] (switching); 0: C_t = sum_k alpha_k C_k    */
+  int32_t lanes;      /* lanes of a warp that own one sequence; 0 = library picks */
+} kvae_dims;
+
+/* problem inputs shared by all entry points */
+typedef struct kvae_inputs {
+  const float* Y;      /* [B,T,p] observations a_t                                  */
+  const float* U;      /* [B,T,m] controls; NULL = all zeros (model.py:149-150)     */
+  const float* mask;   /* [B,T] 1 = observed, 0 = missing; NULL = all ones          */
+  const float* alpha;  /* [B,T,K] mixture weights                                   */
+  const float* A;      /* [K,n,n]                                                   */
+  const float* Bm;     /* [K,n,m]                                                   */
+  const float* C;      /* [K,p,n]                                                   */
+  const float* Q;      /* [K,n,n] or [n,n] (see q_per_mode)                         */
+  const float* R;      /* [p,p]                                                     */
+  const float* mu0;    /* [n]                                                       */
+  const float* Sigma0; /* [n,n]                                                     */
+  const float* mu_init;    /* [B,n]   optional per-sequence initial belief (NULL = mu0)     */
+  const float* Sigma_init; /* [B,n,n] optional per-sequence initial belief (NULL = Sigma0)  */
+} kvae_inputs;
+
+/* the six state tensors (written by the forward pass, read by ELBO / backward) */
+typedef struct kvae_states {
+  float* mus_filt;      /* [B,T,n]   */
+  float* Sigmas_filt;   /* [B,T,n,n] */
+  float* mus_pred;      /* [B,T,n]   */
+  float* Sigmas_pred;   /* [B,T,n,n] */
+  float* mus_smooth;    /* [B,T,n]   NULL in the forward pass = filter only */
+  float* Sigmas_smooth; /* [B,T,n,n] */
+} kvae_states;
+
+int kvae_abi_version(void);
+const char* kvae_last_error(void); /* thread-local, never NULL */
+
+/* 1 if (n,p,m,K,q_per_mode,c_shared,lanes) is instantiated, else 0 */
+int kvae_supported(const kvae_dims* d);
+/* lanes per sequence the library would use for this problem size */
+int kvae_pick_lanes(const kvae_dims* d);
+
+/* Forward recursion.  A_list [B,T,n,n], B_list [B,T,n,m], C_list [B,T,p,n] may each be NULL
+ * (not materialised). */
+int kvae_kf_filter_smooth_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                              float* A_list, float* B_list, float* C_list,
+                              int32_t* info, int device, void* stream);
+
+/* ELBO of the smoothed posterior with the reparameterised sample z = mu_s + chol(Sigma_s + jitter I) eps.
+ * terms[8] (device, fp32): [0] sum log p(z_t|z_{t-1})  [1] sum mask*log p(y_t|z_t)  [2] sum log p(z_0)
+ *   [3] sum entropy  [4] sum(mask)  [5] elbo = ([0]+[1]+[2]+[3]) / max([4],1)  [6] 1/max([4],1)  [7] 0
+ * workspace: kvae_kf_elbo_workspace_bytes(d) bytes of device scratch. */
+size_t kvae_kf_elbo_workspace_bytes(const kvae_dims* d);
+int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                     const float* eps, float jitter, float* terms, void* workspace,
+                     int32_t* info, int device, void* stream);
+
+/* Cotangents of the nine `smooth` outputs (each may be NULL = zero). */
+typedef struct kvae_cotangents {
+  const float* mus_smooth;    const float* Sigmas_smooth;
+  const float* mus_filt;      const float* Sigmas_filt;
+  const float* mus_pred;      const float* Sigmas_pred;
+  const float* A_list;        const float* B_list;        const float* C_list;
+} kvae_cotangents;
+
+typedef struct kvae_grads {
+  float* dY;      /* [B,T,p]                                              */
+  float* dU;      /* [B,T,m]  may be NULL                                 */
+  float* dalpha;  /* [B,T,K]                                              */
+  float* dA;      /* [K,n,n]                                              */
+  float* dBm;     /* [K,n,m]                                              */
+  float* dC;      /* [K,p,n]  (c_shared: only dC[0] is non-zero)          */
+  float* dQ;      /* [K,n,n]  q_per_mode only; else may be NULL           */
+} kvae_grads;
+
+/* Explicit adjoint (reverse-time) pass: gradient of
+ *     g_elbo * elbo  +  sum_i <cot_i, smooth_output_i>
+ * with respect to Y, U, alpha, A, Bm, C, Q.  g_elbo is a DEVICE scalar (NULL = 0: no ELBO term;
+ * then eps/terms may be NULL too); `terms` is the array written by kvae_kf_elbo_fwd (its [6] is
+ * the global normaliser, which under data parallelism the caller overwrites with the all-reduced
+ * value).  `cot` may be NULL.  workspace: kvae_kf_bwd_workspace_bytes(d) bytes. */
+size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d);
+int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                const float* eps, float jitter, const float* g_elbo, const float* terms,
+                const kvae_cotangents* cot, const kvae_grads* grads, void* workspace,
+                int32_t* info, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVAE_KALMAN_H */

@@ -1,0 +1,72 @@
+"""Builds libkvae_kalman.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+One translation unit per shape of kvae_configs.h (compiled in parallel), plus the C-ABI unit.
+No torch headers are involved: the library's only dependency is the CUDA runtime.
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "csrc", "_obj")
+LIB = os.path.join(HERE, "libkvae_kalman.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def shapes():
+    txt = open(os.path.join(CSRC, "kvae_configs.h")).read()
+    body = txt[txt.index("#define KVAE_FOR_EACH_SHAPE"):]
+    return [tuple(int(x) for x in m) for m in re.findall(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", body)]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
+           [os.path.join(HERE, "..", "include", "kvae_kalman.h")]
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(s) <= t for s in _sources())
+
+
+def _run(cmd, log):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + p.stdout)
+    if p.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{p.stdout[-4000:]}")
+    return p.stdout
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    for (n, p, m, k) in shapes():
+        o = os.path.join(OBJ, f"shape_{n}_{p}_{m}_{k}.o")
+        cmd = [NVCC, *ARCH, *FLAGS, f"-DKV_N={n}", f"-DKV_P={p}", f"-DKV_M={m}", f"-DKV_K={k}",
+               "-c", os.path.join(CSRC, "kvae_shape.cu"), "-o", o]
+        jobs.append((cmd, o))
+    o = os.path.join(OBJ, "capi.o")
+    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_capi.cu"), "-o", o], o))
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
+    if verbose:
+        for out in outs:
+            sys.stdout.write(out)
+    _run([NVCC, *ARCH, "-shared", "-o", LIB, *[j[1] for j in jobs]], os.path.join(OBJ, "link.log"))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,164 @@
+"""ctypes binding of libkvae_kalman.so (include/kvae_kalman.h) for torch CUDA tensors.
+
+This is the only place the package touches the native library.  There is no fallback: if the
+library is missing or the tensors are not CUDA tensors the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkvae_kalman.so")
+
+
+class KvaeDims(Structure):
+    _fields_ = [(k, c_int32) for k in ("B", "T", "n", "p", "m", "K", "q_per_mode", "c_shared", "lanes")]
+
+
+class KvaeInputs(Structure):
+    _fields_ = [(k, c_void_p) for k in ("Y", "U", "mask", "alpha", "A", "Bm", "C", "Q", "R", "mu0", "Sigma0",
+                                        "mu_init", "Sigma_init")]
+
+
+class KvaeStates(Structure):
+    _fields_ = [(k, c_void_p) for k in ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
+                                        "mus_smooth", "Sigmas_smooth")]
+
+
+class KvaeCotangents(Structure):
+    _fields_ = [(k, c_void_p) for k in ("mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt",
+                                        "mus_pred", "Sigmas_pred", "A_list", "B_list", "C_list")]
+
+
+class KvaeGrads(Structure):
+    _fields_ = [(k, c_void_p) for k in ("dY", "dU", "dalpha", "dA", "dBm", "dC", "dQ")]
+
+
+class KvaeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads the native library (raises if it has not been built: there is no CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KvaeError(
+            f"{LIB_PATH} not found: build it with `python -m kalman_vae_b200.build` "
+            "(or __graft_entry__.build()). The Kalman hot path has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.kvae_abi_version.restype = c_int
+    L.kvae_last_error.restype = c_char_p
+    L.kvae_supported.argtypes = [POINTER(KvaeDims)]
+    L.kvae_pick_lanes.argtypes = [POINTER(KvaeDims)]
+    L.kvae_kf_filter_smooth_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates),
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.kvae_kf_elbo_workspace_bytes.argtypes = [POINTER(KvaeDims)]
+    L.kvae_kf_elbo_workspace_bytes.restype = c_size_t
+    L.kvae_kf_elbo_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.kvae_kf_bwd_workspace_bytes.argtypes = [POINTER(KvaeDims)]
+    L.kvae_kf_bwd_workspace_bytes.restype = c_size_t
+    L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
+                              c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads), c_void_p,
+                              c_void_p, c_int, c_void_p]
+    if L.kvae_abi_version() != 1:
+        raise KvaeError("libkvae_kalman.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
+    "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
+    "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
+]
+
+
+def _ptr(t, name, device=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise KvaeError(f"{name}: expected a CUDA tensor (the Kalman hot path has no CPU implementation)")
+    if t.dtype != torch.float32 and t.dtype != torch.int32:
+        raise KvaeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise KvaeError(f"{name}: expected a contiguous tensor")
+    if t.data_ptr() % 16 != 0:
+        raise KvaeError(f"{name}: base pointer must be 16-byte aligned")
+    if device is not None and t.device != device:
+        raise KvaeError(f"{name}: on {t.device}, expected {device}")
+    return c_void_p(t.data_ptr())
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise KvaeError(f"{what} failed (status {rc}): {lib().kvae_last_error().decode()}")
+
+
+def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0):
+    return KvaeDims(B, T, n, p, m, K, int(bool(q_per_mode)), int(bool(c_shared)), int(lanes))
+
+
+def supported(dims) -> bool:
+    return bool(lib().kvae_supported(byref(dims)))
+
+
+def pick_lanes(dims) -> int:
+    return int(lib().kvae_pick_lanes(byref(dims)))
+
+
+def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Sigma_init=None):
+    dev = Y.device
+    names = ("Y", "U", "mask", "alpha", "A", "Bm", "C", "Q", "R", "mu0", "Sigma0", "mu_init", "Sigma_init")
+    vals = (Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init, Sigma_init)
+    return KvaeInputs(*[_ptr(v, k, dev) for k, v in zip(names, vals)])
+
+
+def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None):
+    names = ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "mus_smooth", "Sigmas_smooth")
+    vals = (mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth, Sigmas_smooth)
+    return KvaeStates(*[_ptr(v, k) for k, v in zip(names, vals)])
+
+
+def _stream(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def filter_smooth_fwd(dims, inputs, states, A_list, B_list, C_list, info, device):
+    rc = lib().kvae_kf_filter_smooth_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"),
+                                         _ptr(B_list, "B_list"), _ptr(C_list, "C_list"), _ptr(info, "info"),
+                                         device.index, _stream(device))
+    _check(rc, "kvae_kf_filter_smooth_fwd")
+
+
+def elbo_workspace_bytes(dims) -> int:
+    return int(lib().kvae_kf_elbo_workspace_bytes(byref(dims)))
+
+
+def elbo_fwd(dims, inputs, states, eps, jitter, terms, workspace, info, device):
+    rc = lib().kvae_kf_elbo_fwd(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
+                                _ptr(terms, "terms"), c_void_p(workspace.data_ptr()), _ptr(info, "info"),
+                                device.index, _stream(device))
+    _check(rc, "kvae_kf_elbo_fwd")
+
+
+def bwd_workspace_bytes(dims) -> int:
+    return int(lib().kvae_kf_bwd_workspace_bytes(byref(dims)))
+
+
+def bwd(dims, inputs, states, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device):
+    cot_s = KvaeCotangents(*[_ptr(cot.get(k) if cot else None, "cot." + k) for k, _ in KvaeCotangents._fields_])
+    grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
+    rc = lib().kvae_kf_bwd(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
+                           _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(cot_s), byref(grads_s),
+                           c_void_p(workspace.data_ptr()), _ptr(info, "info"), device.index, _stream(device))
+    _check(rc, "kvae_kf_bwd")

@@ -1,0 +1,150 @@
+// kvae_capi.cu — the extern "C" boundary declared in include/kvae_kalman.h.
+#include <cstdio>
+#include <cstring>
+#include "kvae_configs.h"
+#include "kvae_ops.h"
+
+namespace {
+thread_local char g_err[256] = "";
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0) { cudaGetDevice(&prev); if (prev != dev) { cudaSetDevice(dev); switched = true; } }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+bool variant_ok(const kvae_dims& d) { return (d.q_per_mode != 0) == (d.c_shared != 0); }
+
+// smallest instantiated lane count that still gives >= 8 warps per SM, else the widest
+int pick_lanes(const kvae_dims& d) {
+  const int n = d.n;
+  int cands[3]; int nc = 0;
+  if (n <= 4) { cands[nc++] = 1; if (n >= 2) cands[nc++] = 2; if (n == 4) cands[nc++] = 4; }
+  else if (n == 8) { cands[nc++] = 4; cands[nc++] = 8; }
+  else { cands[nc++] = n / 2; cands[nc++] = n; }
+  const long want_threads = 148L * 8 * 32;
+  for (int i = 0; i < nc; ++i) if ((long)d.B * cands[i] >= want_threads) return cands[i];
+  return cands[nc - 1];
+}
+}  // namespace
+
+
+extern "C" {
+
+int kvae_abi_version(void) { return KVAE_ABI_VERSION; }
+const char* kvae_last_error(void) { return g_err; }
+
+int kvae_pick_lanes(const kvae_dims* d) { return d ? pick_lanes(*d) : 0; }
+
+int kvae_supported(const kvae_dims* d) {
+  if (!d || !variant_ok(*d)) return 0;
+  const int lanes = d->lanes ? d->lanes : pick_lanes(*d);
+#define X(n_, p_, m_, k_) \
+  if (d->n == n_ && d->p == p_ && d->m == m_ && d->K == k_) return kvae::ShapeOps<n_, p_, m_, k_>::lanes_ok(lanes) ? 1 : 0;
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return 0;
+}
+
+static int check_common(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, kvae_dims* dd) {
+  if (!d || !in || !st) return fail(-1, "null argument");
+  if (d->B <= 0 || d->T <= 0) return fail(-1, "B and T must be positive");
+  if (!variant_ok(*d)) return fail(-2, "unsupported variant: q_per_mode and c_shared must both be 0 (lstm) or 1 (switching)");
+  *dd = *d;
+  if (dd->lanes == 0) dd->lanes = pick_lanes(*dd);
+  if (!kvae_supported(dd)) return fail(-2, "unsupported (n,p,m,K,lanes): see kvae_configs.h");
+  if (!in->Y || !in->alpha || !in->A || !in->Bm || !in->C || !in->Q || !in->R || !in->mu0 || !in->Sigma0)
+    return fail(-1, "null input tensor");
+  if (!st->mus_filt || !st->Sigmas_filt || !st->mus_pred || !st->Sigmas_pred) return fail(-1, "null state tensor");
+  return 0;
+}
+
+int kvae_kf_filter_smooth_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, float* A_list,
+                              float* B_list, float* C_list, int32_t* info, int device, void* stream) {
+  kvae_dims dd;
+  if (int rc = check_common(d, in, st, &dd)) return rc;
+  if (!info) return fail(-1, "info must not be null");
+  if ((st->mus_smooth == nullptr) != (st->Sigmas_smooth == nullptr)) return fail(-1, "mus_smooth/Sigmas_smooth: both or neither");
+  DeviceGuard guard(device);
+#define X(n_, p_, m_, k_)                                                                                   \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
+    int rc = kvae::ShapeOps<n_, p_, m_, k_>::fwd(dd, *in, *st, A_list, B_list, C_list, info, (cudaStream_t)stream); \
+    if (rc > 0) return fail(rc, cudaGetErrorString((cudaError_t)rc));                                       \
+    if (rc < 0) return fail(rc, "forward launch rejected");                                                 \
+    return 0;                                                                                               \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return fail(-2, "unsupported shape");
+}
+
+size_t kvae_kf_elbo_workspace_bytes(const kvae_dims* d) {
+  if (!d) return 0;
+  kvae_dims dd = *d;
+  if (dd.lanes == 0) dd.lanes = pick_lanes(dd);
+#define X(n_, p_, m_, k_) \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) return kvae::ShapeOps<n_, p_, m_, k_>::elbo_ws(dd);
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return 0;
+}
+
+int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                     float* terms, void* workspace, int32_t* info, int device, void* stream) {
+  kvae_dims dd;
+  if (int rc = check_common(d, in, st, &dd)) return rc;
+  if (!info || !eps || !terms || !workspace) return fail(-1, "null argument");
+  if (!st->mus_smooth || !st->Sigmas_smooth) return fail(-1, "smoothed states required");
+  DeviceGuard guard(device);
+#define X(n_, p_, m_, k_)                                                                                   \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
+    int rc = kvae::ShapeOps<n_, p_, m_, k_>::elbo(dd, *in, *st, eps, jitter, terms, workspace, info, (cudaStream_t)stream); \
+    if (rc > 0) return fail(rc, cudaGetErrorString((cudaError_t)rc));                                       \
+    if (rc < 0) return fail(rc, "elbo launch rejected");                                                    \
+    return 0;                                                                                               \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return fail(-2, "unsupported shape");
+}
+
+size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d) {
+  if (!d) return 0;
+  kvae_dims dd = *d;
+  if (dd.lanes == 0) dd.lanes = pick_lanes(dd);
+#define X(n_, p_, m_, k_) \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) return kvae::ShapeOps<n_, p_, m_, k_>::bwd_ws(dd);
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return 0;
+}
+
+int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                const float* g_elbo, const float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
+                void* workspace, int32_t* info, int device, void* stream) {
+  kvae_dims dd;
+  if (int rc = check_common(d, in, st, &dd)) return rc;
+  if (!info || !grads || !workspace) return fail(-1, "null argument");
+  if (!st->mus_smooth || !st->Sigmas_smooth) return fail(-1, "smoothed states required");
+  if (g_elbo && (!eps || !terms)) return fail(-1, "g_elbo given without eps/terms");
+  if (!grads->dY || !grads->dalpha || !grads->dA || !grads->dBm || !grads->dC) return fail(-1, "null gradient buffer");
+  if (dd.q_per_mode && !grads->dQ) return fail(-1, "dQ required when q_per_mode");
+  DeviceGuard guard(device);
+  kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace};
+#define X(n_, p_, m_, k_)                                                                                   \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
+    int rc = kvae::ShapeOps<n_, p_, m_, k_>::bwd(dd, *in, *st, x, info, (cudaStream_t)stream);             \
+    if (rc > 0) return fail(rc, cudaGetErrorString((cudaError_t)rc));                                       \
+    if (rc < 0) return fail(rc, "backward launch rejected");                                                \
+    return 0;                                                                                               \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return fail(-2, "unsupported shape");
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// kvae_fwd.cuh — forward recursion of the Kalman hot path, one sequence per lane group.
+//
+//   sweep 1 (t = 0..T-1)  : A.0 mixing + A.1 filter step   (kalman_filter.py:31-104, :107-201;
+//                           dyn_param.py:58-60; switch_dyn_param.py:82-86)
+//   sweep 2 (t = T-2..0)  : A.2 RTS smoother step          (kalman_filter.py:204-237, :240-279)
+//
+// Equation labels (A.x) follow SURVEY.md Appendix A.  Tensor layouts are the reference's
+// batch-major [B,T,...] contiguous fp32 layouts (kalman_filter.py:193-201).
+#pragma once
+#include "kvae_prims.cuh"
+
+namespace kvae {
+
+// Arguments shared by all sweeps (plain pointers; nullable where noted).
+struct Args {
+  int B, T;
+  // inputs
+  const float* Y;      // [B,T,P]
+  const float* U;      // [B,T,M]   nullable -> zeros
+  const float* mask;   // [B,T]     nullable -> ones
+  const float* alpha;  // [B,T,K]
+  const float* eps;    // [B,T,N]   (ELBO / backward)
+  // state tensors (outputs of the forward pass, inputs of ELBO / backward)
+  float* mu_f;   float* Sig_f;   // [B,T,N], [B,T,N,N]
+  float* mu_p;   float* Sig_p;
+  float* mu_s;   float* Sig_s;   // nullable in the forward pass -> filter only
+  float* A_list; float* B_list; float* C_list;  // nullable -> not materialised
+  // optional initial belief per sequence (single-step / chunked filtering); nullable -> mu0/Sigma0
+  const float* mu_init;   // [B,N]
+  const float* Sig_init;  // [B,N,N]
+  int* info;  // device word, set to nonzero if a Cholesky pivot was not positive
+};
+
+constexpr int pad4(int x) { return (x + 3) & ~3; }
+
+// Base parameters staged once per CTA in shared memory (C^T is stored transposed per mode so that
+// a lane's rows of C_t^T are contiguous).
+template <class C> struct Base {
+  static constexpr int oA = 0;
+  static constexpr int oB = oA + pad4(C::K * C::N * C::N);
+  static constexpr int oCt = oB + pad4(C::K * C::N * C::M);
+  static constexpr int oQ = oCt + pad4(C::KC * C::N * C::P);
+  static constexpr int oR = oQ + pad4(C::KQ * C::N * C::N);
+  static constexpr int oMu0 = oR + pad4(C::P * C::P);
+  static constexpr int oS0 = oMu0 + pad4(C::N);
+  static constexpr int total = oS0 + pad4(C::N * C::N);
+};
+
+// element-wise fill of the base block; `i` strides over [0,total) (thread-strided on device)
+template <class C>
+KV_FN void base_fill(float* base, int i, const float* A, const float* Bm, const float* Cm, const float* Q,
+                     const float* Rm, const float* mu0, const float* S0) {
+  using BL = Base<C>;
+  constexpr int N = C::N, P = C::P, M = C::M, K = C::K;
+  float v = 0.f;
+  if (i < BL::oB) { if (i < K * N * N) v = A[i]; }
+  else if (i < BL::oCt) { int j = i - BL::oB; if (j < K * N * M) v = Bm[j]; }
+  else if (i < BL::oQ) {
+    int j = i - BL::oCt;
+    if (j < C::KC * N * P) { int k = j / (N * P), rem = j % (N * P), row = rem / P, a = rem % P; v = Cm[(k * P + a) * N + row]; }
+  }
+  else if (i < BL::oR) { int j = i - BL::oQ; if (j < C::KQ * N * N) v = Q[j]; }
+  else if (i < BL::oMu0) { int j = i - BL::oR; if (j < P * P) v = Rm[j]; }
+  else if (i < BL::oS0) { int j = i - BL::oMu0; if (j < N) v = mu0[j]; }
+  else { int j = i - BL::oS0; if (j < N * N) v = S0[j]; }
+  base[i] = v;
+}
+
+// Per-group scratch tiles (only used when C::MEM).
+template <class C> struct Tiles {
+  static constexpr int szNN = pad4(C::N * ld_of<C::N>::v);
+  static constexpr int szNP = pad4(C::N * ld_of<C::P>::v);
+  static constexpr int oX0 = 0;
+  static constexpr int oX1 = oX0 + szNN;
+  static constexpr int oX2 = oX1 + szNN;
+  static constexpr int oC = oX2 + szNN;
+  static constexpr int oK = oC + szNP;
+  static constexpr int oV = oK + szNP;   // vector all-gather slot (N floats)
+  static constexpr int total = C::MEM ? (oV + pad4(C::N)) : 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// per-step inputs
+// ---------------------------------------------------------------------------------------
+template <class C> struct StepIn {
+  float y[C::P];
+  float u[C::M];
+  float al[C::K];
+  float m;
+};
+template <class C> KV_FN void load_step(const Args& a, long bt, StepIn<C>& s) {
+  load_row<C::P>(a.Y + bt * C::P, s.y);
+  if (a.U) load_row<C::M>(a.U + bt * C::M, s.u);
+  else { KV_UNROLL for (int j = 0; j < C::M; ++j) s.u[j] = 0.f; }
+  load_row<C::K>(a.alpha + bt * C::K, s.al);
+  s.m = a.mask ? a.mask[bt] : 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------
+// A.0  mixing: own rows of A_t, B_t, C_t^T, Q_t
+// ---------------------------------------------------------------------------------------
+template <class C, int COLS>
+KV_FN void mix_one(const float* __restrict__ basek, int modes, const float (&al)[C::K], int row0, float (&out)[C::R][COLS]) {
+  KV_UNROLL for (int r = 0; r < C::R; ++r) KV_UNROLL for (int j = 0; j < COLS; ++j) out[r][j] = 0.f;
+  KV_UNROLL for (int k = 0; k < C::K; ++k) {
+    if (k < modes) {
+      KV_UNROLL for (int r = 0; r < C::R; ++r) {
+        float row[COLS];
+        load_row<COLS>(basek + (k * C::N + row0 + r) * COLS, row);
+        KV_UNROLL for (int j = 0; j < COLS; ++j) out[r][j] = fmaf(al[k], row[j], out[r][j]);
+      }
+    }
+  }
+}
+template <class C, int COLS>
+KV_FN void copy_rows(const float* __restrict__ src, int row0, float (&out)[C::R][COLS]) {
+  KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<COLS>(src + (row0 + r) * COLS, out[r]);
+}
+template <class C> KV_FN void mix_A(const float* base, const float (&al)[C::K], int row0, float (&A)[C::R][C::N]) {
+  mix_one<C, C::N>(base + Base<C>::oA, C::K, al, row0, A);
+}
+template <class C> KV_FN void mix_B(const float* base, const float (&al)[C::K], int row0, float (&Bm)[C::R][C::M]) {
+  mix_one<C, C::M>(base + Base<C>::oB, C::K, al, row0, Bm);
+}
+template <class C> KV_FN void mix_Ct(const float* base, const float (&al)[C::K], int row0, float (&Ct)[C::R][C::P]) {
+  if constexpr (C::CSH) copy_rows<C, C::P>(base + Base<C>::oCt, row0, Ct);
+  else mix_one<C, C::P>(base + Base<C>::oCt, C::K, al, row0, Ct);
+}
+template <class C> KV_FN void mix_Q(const float* base, const float (&al)[C::K], int row0, float (&Q)[C::R][C::N]) {
+  if constexpr (C::QPM) mix_one<C, C::N>(base + Base<C>::oQ, C::K, al, row0, Q);
+  else copy_rows<C, C::N>(base + Base<C>::oQ, row0, Q);
+}
+
+// Everything a filter step recomputes that the adjoint also needs.
+template <class C> struct GainOut {
+  float Pm[C::R][C::P];   // own rows of P = Sigma_p C^T
+  float K0[C::R][C::P];   // unmasked gain rows
+  float Kg[C::R][C::P];   // masked gain rows
+  float r[C::P];          // innovation (replicated)
+  float Lc[C::P][C::P];   // chol(S) (replicated)
+  float invd[C::P];
+};
+
+// gain part of A.1:  S = sym(C Sp C^T + R), K0 = P S^-1, K = m K0, r = y - C mu_p.
+// Ct: own rows of C^T; Ctf: full view of C^T; Sp: own rows of Sigma_p; mup_own: own entries of mu_p.
+template <class C, class VC>
+KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)[C::R][C::N], const float (&mup_own)[C::R],
+                const float (&Ct)[C::R][C::P], const VC& Ctf, const float (&y)[C::P], float m, GainOut<C>& o) {
+  constexpr int P = C::P, R = C::R;
+  mm_RS<false>(Sp, Ctf, o.Pm);  // P[r][a] = sum_j Sp[r][j] Ct[j][a]     (kalman_filter.py:82)
+  // partial S = C P and y_pred = C mu_p over own rows, then all-reduce
+  float red[P * P + P];
+  KV_UNROLL for (int a = 0; a < P; ++a) {
+    KV_UNROLL for (int b = 0; b < P; ++b) {
+      float s = 0.f;
+      KV_UNROLL for (int r = 0; r < R; ++r) s = fmaf(Ct[r][a], o.Pm[r][b], s);
+      red[a * P + b] = s;
+    }
+    float s = 0.f;
+    KV_UNROLL for (int r = 0; r < R; ++r) s = fmaf(Ct[r][a], mup_own[r], s);
+    red[P * P + a] = s;
+  }
+  g.allreduce(red);
+  const float* Rm = base + Base<C>::oR;
+  float S[P][P];
+  KV_UNROLL for (int a = 0; a < P; ++a) KV_UNROLL for (int b = 0; b < P; ++b) S[a][b] = red[a * P + b] + Rm[a * P + b];  // :78
+  float Ss[P][P];
+  KV_UNROLL for (int a = 0; a < P; ++a) KV_UNROLL for (int b = 0; b < P; ++b) Ss[a][b] = 0.5f * (S[a][b] + S[b][a]);     // :79
+  const bool ok = chol_small<P>(Ss, o.Lc, o.invd);
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int a = 0; a < P; ++a) o.K0[r][a] = o.Pm[r][a];
+  RegView<P, P> Lv{o.Lc};
+  solve_rows_llt<R, P>(o.K0, Lv, o.invd);                                                    // :89
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int a = 0; a < P; ++a) o.Kg[r][a] = m * o.K0[r][a];  // :92
+  KV_UNROLL for (int a = 0; a < P; ++a) o.r[a] = y[a] - red[P * P + a];                      // :73-75
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep 1: filter.  On return Sig (own rows) and mu (replicated) hold the last filtered belief.
+// ---------------------------------------------------------------------------------------
+template <class C>
+KV_FN void filter_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+                        float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R]) {
+  constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
+  constexpr bool MEM = C::MEM;
+  using TL = Tiles<C>;
+  float* X0 = tiles + TL::oX0; float* X1 = tiles + TL::oX1; float* X2 = tiles + TL::oX2;
+  float* CB = tiles + TL::oC; float* KB = tiles + TL::oK; float* VB = tiles + TL::oV;
+  const int row0 = g.row0();
+  const int T = a.T;
+  bool ok = true;
+
+  // initial belief
+  if (a.Sig_init) { KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_init + ((long)b * N + row0 + r) * N, Sig[r]); }
+  else copy_rows<C, N>(base + Base<C>::oS0, row0, Sig);
+  if (a.mu_init) load_row<N>(a.mu_init + (long)b * N, mu);
+  else load_row<N>(base + Base<C>::oMu0, mu);
+
+  StepIn<C> cur, nxt;
+  load_step<C>(a, (long)b * T, cur);
+  for (int t = 0; t < T; ++t) {
+    const long bt = (long)b * T + t;
+    if (t + 1 < T) load_step<C>(a, bt + 1, nxt);  // software prefetch of the next step's inputs
+
+    float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
+    mix_A<C>(base, cur.al, row0, A);
+    mix_B<C>(base, cur.al, row0, Bm);
+    mix_Ct<C>(base, cur.al, row0, Ct);
+    mix_Q<C>(base, cur.al, row0, Q);
+
+    // predict (A.1): mu_p = A mu + B u ; Sigma_p = (A Sigma) A^T + Q        (kalman_filter.py:65-67)
+    float mup[R];
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s1 = 0.f, s2 = 0.f;
+      KV_UNROLL for (int j = 0; j < N; ++j) s1 = fmaf(A[r][j], mu[j], s1);
+      KV_UNROLL for (int j = 0; j < M; ++j) s2 = fmaf(Bm[r][j], cur.u[j], s2);
+      mup[r] = s1 + s2;
+    }
+    float Sp[R][N];
+    {
+      auto Sf_v = publish<MEM, L, R, N>(g, Sig, X0);
+      float Mx[R][N];
+      mm_RS<false>(A, Sf_v, Mx);
+      auto A_v = publish<MEM, L, R, N>(g, A, X1);
+      mm_RSt<false>(Mx, A_v, Sp);
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sp[r][j] += Q[r][j];
+    }
+    // update
+    auto Ct_v = publish<MEM, L, R, P>(g, Ct, CB);
+    GainOut<C> go;
+    ok = gain<C>(g, base, Sp, mup, Ct, Ct_v, cur.y, cur.m, go) && ok;
+    float muf[R];
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+      KV_UNROLL for (int q = 0; q < P; ++q) s = fmaf(go.Kg[r][q], go.r[q], s);
+      muf[r] = mup[r] + s;                                                     // :96
+    }
+    // Joseph form: Sigma_f = sym((G Sp) G^T + (K R) K^T), G = I - K C          (:99-101)
+    float G[R][N];
+    mm_RSt<false>(go.Kg, Ct_v, G);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) G[r][j] = ((row0 + r == j) ? 1.0f : 0.0f) - G[r][j];
+    float Xm[R][N];
+    {
+      auto Sp_v = publish<MEM, L, R, N>(g, Sp, X2);
+      float T1[R][N];
+      mm_RS<false>(G, Sp_v, T1);
+      auto G_v = publish<MEM, L, R, N>(g, G, X1);
+      mm_RSt<false>(T1, G_v, Xm);
+      float KR[R][P];
+      const float* Rm = base + Base<C>::oR;
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int q = 0; q < P; ++q) {
+        float s = 0.f;
+        KV_UNROLL for (int q2 = 0; q2 < P; ++q2) s = fmaf(go.Kg[r][q2], Rm[q2 * P + q], s);
+        KR[r][q] = s;
+      }
+      auto K_v = publish<MEM, L, R, P>(g, go.Kg, KB);
+      float KRK[R][N];
+      mm_RSt<false>(KR, K_v, KRK);
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] += KRK[r][j];
+    }
+    float Sf[R][N];
+    {
+      auto X_v = publish<MEM, L, R, N>(g, Xm, X0);
+      float Xt[R][N];
+      tr_rows<R, N>(X_v, row0, Xt);
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sf[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
+    }
+
+    if (active) {
+      KV_UNROLL for (int r = 0; r < R; ++r) {
+        store_row<N>(a.Sig_p + (bt * N + row0 + r) * N, Sp[r]);
+        store_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);
+      }
+      store_row<R>(a.mu_p + bt * N + row0, mup);
+      store_row<R>(a.mu_f + bt * N + row0, muf);
+      if (a.A_list) { KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.A_list + (bt * N + row0 + r) * N, A[r]); }
+      if (a.B_list) { KV_UNROLL for (int r = 0; r < R; ++r) store_row<M>(a.B_list + (bt * N + row0 + r) * M, Bm[r]); }
+      if (a.C_list) {
+        if constexpr (L == 1) {
+          KV_UNROLL for (int q = 0; q < P; ++q) {
+            float crow[N];
+            KV_UNROLL for (int j = 0; j < N; ++j) crow[j] = Ct[j][q];
+            store_row<N>(a.C_list + (bt * P + q) * N, crow);
+          }
+        } else {
+          KV_UNROLL for (int q = 0; q < P; ++q) KV_UNROLL for (int r = 0; r < R; ++r) a.C_list[(bt * P + q) * N + row0 + r] = Ct[r][q];
+        }
+      }
+    }
+    // carry
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = Sf[r][j];
+    allgather<MEM, L, R>(g, muf, VB, mu);
+    KV_UNROLL for (int r = 0; r < R; ++r) mu_own[r] = muf[r];
+    cur = nxt;
+  }
+  if (!ok && active) *a.info = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// smoother gain (A.2), shared with the adjoint:  J = (Sf A1^T) Sp1^-1 with a general (unsymmetric)
+// LU of Sp1, as the reference does (kalman_filter.py:229).  On return LU (own rows) / invu hold the
+// factor and XL holds its published copy.
+// ---------------------------------------------------------------------------------------
+template <class C>
+KV_FN bool smoother_gain(const Group<C::L, C::R>& g, float* XA, float* XL, const float (&Sf)[C::R][C::N],
+                         const float (&A1)[C::R][C::N], const float (&Sp1)[C::R][C::N], float (&J)[C::R][C::N],
+                         float (&LU)[C::R][C::N], float (&invu)[C::N]) {
+  constexpr int N = C::N, R = C::R, L = C::L;
+  auto A_v = publish<C::MEM, L, R, N>(g, A1, XA);
+  mm_RSt<false>(Sf, A_v, J);                                 // W = Sf A1^T
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) LU[r][j] = Sp1[r][j];
+  const bool ok = lu_dist<L, R>(g, LU, invu);
+  auto L_v = publish<C::MEM, L, R, N>(g, LU, XL);
+  solve_rows_lu<R, N>(J, L_v, invu);                         // J = W Sp1^-1
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep 2: RTS smoother, t = T-2..0.  Sig / mus (own rows / entries) enter as the last filtered
+// belief (= smoothed belief at T-1).
+// ---------------------------------------------------------------------------------------
+template <class C>
+KV_FN void smoother_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+                          float (&Sig)[C::R][C::N], float (&mus)[C::R]) {
+  constexpr int N = C::N, R = C::R, L = C::L;
+  constexpr bool MEM = C::MEM;
+  using TL = Tiles<C>;
+  float* X0 = tiles + TL::oX0; float* X1 = tiles + TL::oX1; float* X2 = tiles + TL::oX2; float* VB = tiles + TL::oV;
+  const int row0 = g.row0();
+  const int T = a.T;
+  bool ok = true;
+  {  // t = T-1: copied, not symmetrised (kalman_filter.py:251-256)
+    const long bt = (long)b * T + (T - 1);
+    if (active) {
+      KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Sig[r]);
+      store_row<R>(a.mu_s + bt * N + row0, mus);
+    }
+  }
+  for (int t = T - 2; t >= 0; --t) {
+    const long bt = (long)b * T + t;
+    float al1[C::K];
+    load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
+    float Sf[R][N], Sp1[R][N], muf[R], mup1[R];
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      load_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);
+      load_row<N>(a.Sig_p + ((bt + 1) * N + row0 + r) * N, Sp1[r]);
+    }
+    load_row<R>(a.mu_f + bt * N + row0, muf);
+    load_row<R>(a.mu_p + (bt + 1) * N + row0, mup1);
+    float A1[R][N];
+    mix_A<C>(base, al1, row0, A1);
+    float J[R][N], LU[R][N], invu[N];
+    ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu) && ok;
+    // mu_s = mu_f + J (mu_s1 - mu_p1)                                            (:232)
+    float d_own[R], d[N];
+    KV_UNROLL for (int r = 0; r < R; ++r) d_own[r] = mus[r] - mup1[r];
+    allgather<MEM, L, R>(g, d_own, VB, d);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+      KV_UNROLL for (int j = 0; j < N; ++j) s = fmaf(J[r][j], d[j], s);
+      mus[r] = muf[r] + s;
+    }
+    // Sigma_s = sym(Sf + (J D) J^T), D = Sigma_s1 - Sp1                          (:234-235)
+    float D[R][N];
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) D[r][j] = Sig[r][j] - Sp1[r][j];
+    float Xm[R][N];
+    {
+      auto D_v = publish<MEM, L, R, N>(g, D, X2);
+      float T1[R][N];
+      mm_RS<false>(J, D_v, T1);
+      auto J_v = publish<MEM, L, R, N>(g, J, X0);
+      mm_RSt<false>(T1, J_v, Xm);
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] = Sf[r][j] + Xm[r][j];
+    }
+    {
+      auto X_v = publish<MEM, L, R, N>(g, Xm, X1);
+      float Xt[R][N];
+      tr_rows<R, N>(X_v, row0, Xt);
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
+    }
+    if (active) {
+      KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Sig[r]);
+      store_row<R>(a.mu_s + bt * N + row0, mus);
+    }
+  }
+  if (!ok && active) *a.info = 1;
+}
+
+}  // namespace kvae

@@ -1,0 +1,26 @@
+// kvae_ops.h — internal interface between the C ABI (kvae_capi.cu) and the per-shape
+// translation units (kvae_shape.cu compiled once per KVAE_FOR_EACH_SHAPE entry).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/kvae_kalman.h"
+
+namespace kvae {
+
+struct BwdExtra {
+  const float* eps; float jitter; const float* g_elbo; const float* terms;
+  const kvae_cotangents* cot; const kvae_grads* grads; void* workspace;
+};
+
+template <int N, int P, int M, int K> struct ShapeOps {
+  static bool lanes_ok(int lanes);
+  static int fwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
+                 float* C_list, int32_t* info, cudaStream_t s);
+  static size_t elbo_ws(const kvae_dims& d);
+  static int elbo(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const float* eps, float jitter,
+                  float* terms, void* ws, int32_t* info, cudaStream_t s);
+  static size_t bwd_ws(const kvae_dims& d);
+  static int bwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const BwdExtra& x, int32_t* info,
+                 cudaStream_t s);
+};
+
+}  // namespace kvae

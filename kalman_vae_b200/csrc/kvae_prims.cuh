@@ -1,0 +1,403 @@
+// kvae_prims.cuh — row-distributed small-matrix primitives for the Kalman hot path.
+//
+// A sequence is owned by a GROUP of L lanes of one warp.  Every n-row matrix of the recursion
+// (Sigma, A_t, B_t, C_t^T, K, J, ...) is distributed by rows: lane l of the group holds rows
+// [l*R, l*R+R), R = n/L, in registers.  A product needs one operand "fully visible"; for L>1
+// that operand is PUBLISHED into a per-group shared-memory tile (row stride padded so that
+// 128-bit row writes and broadcast row reads are bank-conflict free) and read back with
+// 128-bit broadcast loads; for L==1 the "view" simply aliases the registers, so the whole
+// recursion runs out of the register file with no shared-memory traffic at all.
+//
+// The same header compiles for the host (L==1 only): tests/hostsim builds it with g++ to check
+// the arithmetic against the oracle on the CPU-only build box.  That build is test tooling and
+// is never loaded by the package.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KV_FN __host__ __device__ __forceinline__
+#else
+#define KV_FN inline __attribute__((always_inline))
+#endif
+#if defined(__CUDA_ARCH__)
+#define KV_UNROLL _Pragma("unroll")
+#else
+#define KV_UNROLL
+#endif
+
+namespace kvae {
+
+struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
+
+// ---------------------------------------------------------------------------------------
+// Static problem description.
+//   N,P,M,K : z_dim, a_dim, u_dim, number of mixture modes
+//   L       : lanes per sequence (divides N); R rows per lane
+//   QPM     : Q_t = sum_k alpha_k Q_k (switching) instead of one fixed Q (lstm)
+//   CSH     : C_t = C_0 (switching) instead of sum_k alpha_k C_k
+//   FM      : force the shared-memory ("published") code path even for L==1 (host tests)
+// ---------------------------------------------------------------------------------------
+template <int N_, int P_, int M_, int K_, int L_, bool QPM_, bool CSH_, bool FM_ = false>
+struct Cfg {
+  static constexpr int N = N_, P = P_, M = M_, K = K_, L = L_, R = N_ / L_;
+  static constexpr bool QPM = QPM_, CSH = CSH_;
+  static constexpr bool MEM = (L_ > 1) || FM_;
+  static constexpr int KC = CSH_ ? 1 : K_;
+  static constexpr int KQ = QPM_ ? K_ : 1;
+  static_assert(N_ % L_ == 0, "lanes per sequence must divide z_dim");
+  static_assert(L_ == 1 || L_ == 2 || L_ == 4 || L_ == 8 || L_ == 16 || L_ == 32, "L must be a power of two <= 32");
+};
+
+// padded leading dimension of a published [rows x COLS] tile
+template <int COLS> struct ld_of { static constexpr int v = (COLS % 8 == 0) ? COLS + 4 : COLS; };
+
+// ---------------------------------------------------------------------------------------
+// vector row access (16-byte when the row length allows it)
+// ---------------------------------------------------------------------------------------
+template <int COLS> KV_FN void load_row(const float* __restrict__ p, float (&o)[COLS]) {
+  if constexpr (COLS % 4 == 0) {
+    KV_UNROLL for (int q = 0; q < COLS / 4; ++q) {
+      f4 v = *reinterpret_cast<const f4*>(p + 4 * q);
+      o[4 * q] = v.x; o[4 * q + 1] = v.y; o[4 * q + 2] = v.z; o[4 * q + 3] = v.w;
+    }
+  } else if constexpr (COLS % 2 == 0) {
+    KV_UNROLL for (int q = 0; q < COLS / 2; ++q) {
+      f2 v = *reinterpret_cast<const f2*>(p + 2 * q);
+      o[2 * q] = v.x; o[2 * q + 1] = v.y;
+    }
+  } else {
+    KV_UNROLL for (int q = 0; q < COLS; ++q) o[q] = p[q];
+  }
+}
+template <int COLS> KV_FN void store_row(float* __restrict__ p, const float (&o)[COLS]) {
+  if constexpr (COLS % 4 == 0) {
+    KV_UNROLL for (int q = 0; q < COLS / 4; ++q) {
+      f4 v; v.x = o[4 * q]; v.y = o[4 * q + 1]; v.z = o[4 * q + 2]; v.w = o[4 * q + 3];
+      *reinterpret_cast<f4*>(p + 4 * q) = v;
+    }
+  } else if constexpr (COLS % 2 == 0) {
+    KV_UNROLL for (int q = 0; q < COLS / 2; ++q) {
+      f2 v; v.x = o[2 * q]; v.y = o[2 * q + 1];
+      *reinterpret_cast<f2*>(p + 2 * q) = v;
+    }
+  } else {
+    KV_UNROLL for (int q = 0; q < COLS; ++q) p[q] = o[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Group of L lanes
+// ---------------------------------------------------------------------------------------
+template <int L, int R> struct Group {
+  int lane;  // lane within the group
+  KV_FN int row0() const { return L == 1 ? 0 : lane * R; }
+  KV_FN void sync() const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (L > 1) __syncwarp();
+#endif
+  }
+  // value held by lane `src` of this group
+  KV_FN float bcast(float v, int src) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (L > 1) return __shfl_sync(0xffffffffu, v, src, L);
+#endif
+    (void)src;
+    return v;
+  }
+  // butterfly all-reduce: every lane ends with the bit-identical sum
+  template <int CNT> KV_FN void allreduce(float (&v)[CNT]) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (L > 1) {
+      KV_UNROLL for (int off = L / 2; off >= 1; off >>= 1) {
+        KV_UNROLL for (int i = 0; i < CNT; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+      }
+    }
+#endif
+  }
+  KV_FN float allreduce1(float v) const {
+    float a[1] = {v};
+    allreduce(a);
+    return a[0];
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Fully visible matrix views
+// ---------------------------------------------------------------------------------------
+template <int ROWS, int COLS> struct MemView {  // tile in shared (or host) memory
+  static constexpr int LD = ld_of<COLS>::v;
+  const float* p;
+  KV_FN float at(int r, int c) const { return p[r * LD + c]; }
+  KV_FN void row(int r, float (&o)[COLS]) const { load_row<COLS>(p + r * LD, o); }
+};
+template <int ROWS, int COLS> struct RegView {  // alias of a register array (L == 1)
+  const float (*v)[COLS];
+  KV_FN float at(int r, int c) const { return v[r][c]; }
+  KV_FN void row(int r, float (&o)[COLS]) const {
+    KV_UNROLL for (int c = 0; c < COLS; ++c) o[c] = v[r][c];
+  }
+};
+template <bool MEM, int ROWS, int COLS> struct view_of { using type = RegView<ROWS, COLS>; };
+template <int ROWS, int COLS> struct view_of<true, ROWS, COLS> { using type = MemView<ROWS, COLS>; };
+
+// publish the lane's R rows of an [L*R x COLS] matrix; returns the full view.
+// For RegView the view ALIASES x: x must stay unmodified while the view is in use.
+template <bool MEM, int L, int R, int COLS>
+KV_FN typename view_of<MEM, L * R, COLS>::type publish(const Group<L, R>& g, const float (&x)[R][COLS], float* buf) {
+  if constexpr (MEM) {
+    constexpr int LD = ld_of<COLS>::v;
+    g.sync();  // everyone finished reading the previous contents of buf
+    KV_UNROLL for (int r = 0; r < R; ++r) store_row<COLS>(buf + (g.row0() + r) * LD, x[r]);
+    g.sync();
+    return MemView<L * R, COLS>{buf};
+  } else {
+    (void)g; (void)buf;
+    return RegView<L * R, COLS>{x};
+  }
+}
+
+// all-gather of a distributed n-vector (lane holds R entries) into a replicated one
+template <bool MEM, int L, int R>
+KV_FN void allgather(const Group<L, R>& g, const float (&x)[R], float* vbuf, float (&full)[L * R]) {
+  if constexpr (MEM) {
+    g.sync();
+    KV_UNROLL for (int r = 0; r < R; ++r) vbuf[g.row0() + r] = x[r];
+    g.sync();
+    load_row<L * R>(vbuf, full);
+  } else {
+    (void)g; (void)vbuf;
+    KV_UNROLL for (int r = 0; r < R; ++r) full[r] = x[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// products.  X: local rows; Y / Xv: fully visible views.
+// ---------------------------------------------------------------------------------------
+// C[r][j] (+)= sum_k X[r][k] * Y(k,j)
+template <bool ACC, int R, int KD, int NC, class V>
+KV_FN void mm_RS(const float (&X)[R][KD], const V& Y, float (&C)[R][NC]) {
+  if constexpr (!ACC) {
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = 0.f;
+  }
+  KV_UNROLL for (int k = 0; k < KD; ++k) {
+    float yr[NC];
+    Y.row(k, yr);
+    KV_UNROLL for (int r = 0; r < R; ++r)
+      KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = fmaf(X[r][k], yr[j], C[r][j]);
+  }
+}
+// C[r][j] (+)= sum_k X[r][k] * Y(j,k)
+template <bool ACC, int R, int KD, int NC, class V>
+KV_FN void mm_RSt(const float (&X)[R][KD], const V& Y, float (&C)[R][NC]) {
+  KV_UNROLL for (int j = 0; j < NC; ++j) {
+    float yr[KD];
+    Y.row(j, yr);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = ACC ? C[r][j] : 0.f;
+      KV_UNROLL for (int k = 0; k < KD; ++k) s = fmaf(X[r][k], yr[k], s);
+      C[r][j] = s;
+    }
+  }
+}
+// C[r][j] (+)= sum_k Xv(k, row0+r) * Y(k,j)      (i.e. own rows of Xv^T * Y)
+template <bool ACC, int R, int KD, int NC, class VX, class VY>
+KV_FN void mm_StS(const VX& Xv, int row0, const VY& Y, float (&C)[R][NC]) {
+  if constexpr (!ACC) {
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = 0.f;
+  }
+  KV_UNROLL for (int k = 0; k < KD; ++k) {
+    float yr[NC];
+    Y.row(k, yr);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const float xk = Xv.at(k, row0 + r);
+      KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = fmaf(xk, yr[j], C[r][j]);
+    }
+  }
+}
+// own rows of the transpose: O[r][j] = Xv(j, row0+r)
+template <int R, int NC, class VX> KV_FN void tr_rows(const VX& Xv, int row0, float (&O)[R][NC]) {
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < NC; ++j) O[r][j] = Xv.at(j, row0 + r);
+}
+
+// ---------------------------------------------------------------------------------------
+// Cholesky (lower), replicated small matrix.  Only the lower triangle of a is read.
+// Returns false if a pivot was not positive.
+// ---------------------------------------------------------------------------------------
+template <int D> KV_FN bool chol_small(const float (&a)[D][D], float (&l)[D][D], float (&invd)[D]) {
+  bool ok = true;
+  KV_UNROLL for (int j = 0; j < D; ++j) {
+    float s = a[j][j];
+    KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-l[j][q], l[j][q], s);
+    ok = ok && (s > 0.f);
+    const float d = sqrtf(s);
+    l[j][j] = d;
+    invd[j] = 1.0f / d;
+    KV_UNROLL for (int i = j + 1; i < D; ++i) {
+      float v = a[i][j];
+      KV_UNROLL for (int q = 0; q < j; ++q) v = fmaf(-l[i][q], l[j][q], v);
+      l[i][j] = v * invd[j];
+    }
+    KV_UNROLL for (int i = 0; i < j; ++i) l[i][j] = 0.f;
+  }
+  return ok;
+}
+
+// Row-distributed Cholesky of an [N x N] matrix (N = L*R): lane owns rows row0..row0+R-1 of
+// a (lower triangle read) and of l.  invd (1/diag) is replicated.  Column j is finished by
+// broadcasting the pivot row from its owner lane with warp shuffles.
+template <int L, int R>
+KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l)[R][L * R], float (&invd)[L * R]) {
+  constexpr int N = L * R;
+  bool ok = true;
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) l[r][j] = 0.f;
+  KV_UNROLL for (int j = 0; j < N; ++j) {
+    const int owner = j / R, jr = j % R;
+    float lj[N];  // row j of L, entries q<j (replicated)
+    KV_UNROLL for (int q = 0; q < j; ++q) lj[q] = g.bcast(l[jr][q], owner);
+    float s = g.bcast(a[jr][j], owner);
+    KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-lj[q], lj[q], s);
+    ok = ok && (s > 0.f);
+    const float d = sqrtf(s);
+    invd[j] = 1.0f / d;
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const int i = g.row0() + r;
+      float v = a[r][j];
+      KV_UNROLL for (int q = 0; q < j; ++q) v = fmaf(-l[r][q], lj[q], v);
+      v *= invd[j];
+      l[r][j] = (i > j) ? v : ((i == j) ? d : 0.f);
+    }
+  }
+  return ok;
+}
+
+// x := x (Lc Lc^T)^-1 for each local row (Lc fully visible, invd = 1/diag(Lc) replicated).
+template <int R, int D, class V>
+KV_FN void solve_rows_llt(float (&x)[R][D], const V& Lc, const float (&invd)[D]) {
+  // y Lc^T = b  (forward, dot form with row j)
+  KV_UNROLL for (int j = 0; j < D; ++j) {
+    float lj[D];
+    Lc.row(j, lj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = x[r][j];
+      KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-x[r][q], lj[q], s);
+      x[r][j] = s * invd[j];
+    }
+  }
+  // z Lc = y    (backward, axpy form with row j)
+  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
+    float lj[D];
+    Lc.row(j, lj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const float xj = x[r][j] * invd[j];
+      x[r][j] = xj;
+      KV_UNROLL for (int q = 0; q < j; ++q) x[r][q] = fmaf(-xj, lj[q], x[r][q]);
+    }
+  }
+}
+// x := x Lc^-1 only (solve z Lc = x), rows local
+template <int R, int D, class V>
+KV_FN void solve_rows_l(float (&x)[R][D], const V& Lc, const float (&invd)[D]) {
+  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
+    float lj[D];
+    Lc.row(j, lj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const float xj = x[r][j] * invd[j];
+      x[r][j] = xj;
+      KV_UNROLL for (int q = 0; q < j; ++q) x[r][q] = fmaf(-xj, lj[q], x[r][q]);
+    }
+  }
+}
+// w := Lc^-1 v for a replicated vector (forward substitution)
+template <int D, class V> KV_FN void solve_vec_l(float (&v)[D], const V& Lc, const float (&invd)[D]) {
+  KV_UNROLL for (int j = 0; j < D; ++j) {
+    float lj[D];
+    Lc.row(j, lj);
+    float s = v[j];
+    KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-v[q], lj[q], s);
+    v[j] = s * invd[j];
+  }
+}
+// w := Lc^-T v for a replicated vector (backward substitution, axpy form)
+template <int D, class V> KV_FN void solve_vec_lt(float (&v)[D], const V& Lc, const float (&invd)[D]) {
+  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
+    float lj[D];
+    Lc.row(j, lj);
+    const float xj = v[j] * invd[j];
+    v[j] = xj;
+    KV_UNROLL for (int q = 0; q < j; ++q) v[q] = fmaf(-xj, lj[q], v[q]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Row-distributed LU without pivoting (in place: unit-lower L below the diagonal, U on/above).
+// Used for the smoother gain, whose matrix Sigma_{t+1|t} = A Sigma A^T + Q_t is NOT symmetric when
+// the learnable Q_k are not (switch_dyn_param.py:18-23; the reference solves it with a general LU,
+// kalman_filter.py:229).  Its symmetric part is positive definite, so elimination without pivoting
+// is stable.  invu = 1/diag(U), replicated.  Pivot row k is broadcast from its owner lane.
+// ---------------------------------------------------------------------------------------
+template <int L, int R>
+KV_FN bool lu_dist(const Group<L, R>& g, float (&a)[R][L * R], float (&invu)[L * R]) {
+  constexpr int N = L * R;
+  bool ok = true;
+  KV_UNROLL for (int k = 0; k < N; ++k) {
+    const int owner = k / R, kr = k % R;
+    float uk[N];
+    KV_UNROLL for (int j = k; j < N; ++j) uk[j] = g.bcast(a[kr][j], owner);
+    ok = ok && (uk[k] > 0.f);
+    invu[k] = 1.0f / uk[k];
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const bool below = (g.row0() + r) > k;
+      const float f = below ? a[r][k] * invu[k] : 0.f;
+      a[r][k] = below ? f : a[r][k];
+      KV_UNROLL for (int j = k + 1; j < N; ++j) a[r][j] = fmaf(-f, uk[j], a[r][j]);
+    }
+  }
+  return ok;
+}
+// x := x (LU)^-1 for each local row  (x A = b  ->  y U = b, x L = y; both in axpy form with row j)
+template <int R, int D, class V>
+KV_FN void solve_rows_lu(float (&x)[R][D], const V& LU, const float (&invu)[D]) {
+  KV_UNROLL for (int j = 0; j < D; ++j) {
+    float uj[D];
+    LU.row(j, uj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const float yj = x[r][j] * invu[j];
+      x[r][j] = yj;
+      KV_UNROLL for (int q = j + 1; q < D; ++q) x[r][q] = fmaf(-yj, uj[q], x[r][q]);
+    }
+  }
+  KV_UNROLL for (int j = D - 1; j >= 1; --j) {
+    float lj[D];
+    LU.row(j, lj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      const float xj = x[r][j];
+      KV_UNROLL for (int q = 0; q < j; ++q) x[r][q] = fmaf(-xj, lj[q], x[r][q]);
+    }
+  }
+}
+// x := x (LU)^-T for each local row  (x A^T = b  ->  y U^T = b, x L^T = y; dot form with row j)
+template <int R, int D, class V>
+KV_FN void solve_rows_lut(float (&x)[R][D], const V& LU, const float (&invu)[D]) {
+  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
+    float uj[D];
+    LU.row(j, uj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = x[r][j];
+      KV_UNROLL for (int q = j + 1; q < D; ++q) s = fmaf(-x[r][q], uj[q], s);
+      x[r][j] = s * invu[j];
+    }
+  }
+  KV_UNROLL for (int j = 1; j < D; ++j) {
+    float lj[D];
+    LU.row(j, lj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = x[r][j];
+      KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-x[r][q], lj[q], s);
+      x[r][j] = s;
+    }
+  }
+}
+
+}  // namespace kvae

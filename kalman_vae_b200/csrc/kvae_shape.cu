@@ -1,0 +1,67 @@
+// kvae_shape.cu — compiled once per shape with -DKV_N= -DKV_P= -DKV_M= -DKV_K= ; defines
+// ShapeOps<KV_N,KV_P,KV_M,KV_K> (lane-count and dynamics-variant dispatch).
+#include "kvae_ops.h"
+#include "kvae_kernels.cuh"
+
+namespace kvae {
+
+namespace {
+constexpr int N = KV_N, P = KV_P, M = KV_M, K = KV_K;
+
+// lane counts instantiated for this z_dim (rows per lane R = N / L kept <= 4 for N >= 8)
+#if KV_N <= 4
+#define KV_FOR_EACH_L(X) X(1) X(2) X(KV_N)
+#define KV_L_OK(l) ((l) == 1 || (l) == 2 || (l) == KV_N)
+#elif KV_N == 8
+#define KV_FOR_EACH_L(X) X(4) X(8)
+#define KV_L_OK(l) ((l) == 4 || (l) == 8)
+#else
+#define KV_FOR_EACH_L(X) X(KV_N / 2) X(KV_N)
+#define KV_L_OK(l) ((l) == KV_N / 2 || (l) == KV_N)
+#endif
+
+Args make_args(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, int32_t* info) {
+  Args a{};
+  a.B = d.B; a.T = d.T;
+  a.Y = in.Y; a.U = in.U; a.mask = in.mask; a.alpha = in.alpha;
+  a.mu_f = st.mus_filt; a.Sig_f = st.Sigmas_filt; a.mu_p = st.mus_pred; a.Sig_p = st.Sigmas_pred;
+  a.mu_s = st.mus_smooth; a.Sig_s = st.Sigmas_smooth;
+  a.mu_init = in.mu_init; a.Sig_init = in.Sigma_init;
+  a.info = info;
+  return a;
+}
+BasePtrs make_base(const kvae_inputs& in) { return BasePtrs{in.A, in.Bm, in.C, in.Q, in.R, in.mu0, in.Sigma0}; }
+}  // namespace
+
+template <> bool ShapeOps<N, P, M, K>::lanes_ok(int lanes) { return KV_L_OK(lanes); }
+
+template <>
+int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list,
+                              float* B_list, float* C_list, int32_t* info, cudaStream_t s) {
+  Args a = make_args(d, in, st, info);
+  a.A_list = A_list; a.B_list = B_list; a.C_list = C_list;
+  const BasePtrs bp = make_base(in);
+  const int smooth = (st.mus_smooth != nullptr) ? 1 : 0;
+  const bool sw = d.q_per_mode != 0;
+#define X(l)                                                                                   \
+  if (d.lanes == (l)) {                                                                        \
+    if constexpr (N % (l) == 0) {                                                              \
+      return sw ? launch_fwd<Cfg<N, P, M, K, (l), true, true>>(a, bp, smooth, s)               \
+                : launch_fwd<Cfg<N, P, M, K, (l), false, false>>(a, bp, smooth, s);            \
+    }                                                                                          \
+  }
+  KV_FOR_EACH_L(X)
+#undef X
+  return -3;
+}
+
+template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims&) { return 0; }
+template <>
+int ShapeOps<N, P, M, K>::elbo(const kvae_dims&, const kvae_inputs&, const kvae_states&, const float*, float, float*,
+                               void*, int32_t*, cudaStream_t) { return -4; }
+template <> size_t ShapeOps<N, P, M, K>::bwd_ws(const kvae_dims&) { return 0; }
+template <>
+int ShapeOps<N, P, M, K>::bwd(const kvae_dims&, const kvae_inputs&, const kvae_states&, const BwdExtra&, int32_t*,
+                              cudaStream_t) { return -4; }
+
+}  // namespace kvae
