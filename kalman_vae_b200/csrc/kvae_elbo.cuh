@@ -1,0 +1,182 @@
+// kvae_elbo.cuh — A.3: ELBO of the smoothed posterior (kalman_filter.py:305-401), one sequence per
+// lane group, forward in time.  z_t = mu_s + chol(sym(Sigma_s)+jitter I) eps_t is the reference's
+// rsample (:348-351) with the standard-normal draw eps supplied by the caller.
+#pragma once
+#include "kvae_fwd.cuh"
+
+namespace kvae {
+
+#define KV_LOG2PI 1.8378770664093453f
+
+// own rows of sym(X) (+ jitter on the diagonal)
+template <class C>
+KV_FN void sym_jitter_rows(const Group<C::L, C::R>& g, const float (&X)[C::R][C::N], float* buf, float jitter,
+                           float (&out)[C::R][C::N]) {
+  constexpr int N = C::N, R = C::R;
+  auto X_v = publish<C::MEM, C::L, R, N>(g, X, buf);
+  float Xt[R][N];
+  tr_rows<R, N>(X_v, g.row0(), Xt);
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
+    out[r][j] = 0.5f * (X[r][j] + Xt[r][j]) + ((g.row0() + r == j) ? jitter : 0.f);
+}
+
+// sum over own rows of log(diag) then over the group
+template <class C> KV_FN float logdet_half(const Group<C::L, C::R>& g, const float (&dg)[C::R]) {
+  float s = 0.f;
+  KV_UNROLL for (int r = 0; r < C::R; ++r) s += logf(dg[r]);
+  return g.allreduce1(s);
+}
+
+// constants of the ELBO that do not depend on t
+template <class C> struct ElboConst {
+  float LR[C::P][C::P], invdR[C::P], logdetR;          // chol(R)                         (:373)
+  float LQ[C::R][C::N], invdQ[C::N], logdetQ;          // chol(sym(Q)+jitter I), fixed Q  (:364-365)
+};
+
+template <class C>
+KV_FN bool elbo_const(const Group<C::L, C::R>& g, const float* base, float* xbuf, float jitter, ElboConst<C>& ec) {
+  constexpr int N = C::N, P = C::P, R = C::R;
+  bool ok = true;
+  float Rm[P][P];
+  KV_UNROLL for (int a = 0; a < P; ++a) KV_UNROLL for (int b = 0; b < P; ++b) Rm[a][b] = base[Base<C>::oR + a * P + b];
+  ok = chol_small<P>(Rm, ec.LR, ec.invdR) && ok;
+  ec.logdetR = 0.f;
+  KV_UNROLL for (int a = 0; a < P; ++a) ec.logdetR += logf(ec.LR[a][a]);
+  if constexpr (!C::QPM) {
+    float Q[R][N], Qs[R][N], dg[R];
+    copy_rows<C, N>(base + Base<C>::oQ, g.row0(), Q);
+    sym_jitter_rows<C>(g, Q, xbuf, jitter, Qs);
+    ok = chol_dist<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg) && ok;
+    ec.logdetQ = logdet_half<C>(g, dg);
+  }
+  return ok;
+}
+
+// Per-step pieces of the ELBO that the adjoint recomputes as well.
+template <class C> struct ElboStep {
+  float Ls[C::R][C::N];   // own rows of chol(sym(Sigma_s)+jI)
+  float invd[C::N];
+  float dg[C::R];
+  float z_own[C::R];
+  float z[C::N];          // replicated sample
+};
+
+// z_t for one step: loads Sigma_s / mu_s at index bt (xbuf: [N x N] tile, vbuf: N-vector slot)
+template <class C>
+KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, float* xbuf, float* vbuf, long bt, float jitter,
+                         const float (&eps)[C::N], ElboStep<C>& es) {
+  constexpr int N = C::N, R = C::R;
+  const int row0 = g.row0();
+  float Ss[R][N], Sj[R][N], mus[R];
+  KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Ss[r]);
+  load_row<R>(a.mu_s + bt * N + row0, mus);
+  sym_jitter_rows<C>(g, Ss, xbuf, jitter, Sj);                         // (:287, :293)
+  const bool ok = chol_dist<C::L, R>(g, Sj, es.Ls, es.invd, es.dg);
+  KV_UNROLL for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+    KV_UNROLL for (int q = 0; q < N; ++q) s = fmaf(es.Ls[r][q], eps[q], s);
+    es.z_own[r] = mus[r] + s;                                                    // (:349-351)
+  }
+  allgather<C::MEM, C::L, R>(g, es.z_own, vbuf, es.z);
+  return ok;
+}
+
+// acc: [0] transition  [1] emission  [2] init  [3] entropy  [4] sum(mask)
+template <class C>
+KV_FN void elbo_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+                      float jitter, double (&acc)[5]) {
+  constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
+  constexpr bool MEM = C::MEM;
+  using TL = Tiles<C>;
+  const int row0 = g.row0();
+  const int T = a.T;
+  ElboConst<C> ec;
+  bool ok = elbo_const<C>(g, base, tiles + TL::oX0, jitter, ec);
+  typename view_of<MEM, N, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, tiles + TL::oXP);
+  float zprev[N];
+  KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = 0.f;
+  double s_tr = 0.0, s_em = 0.0, s_in = 0.0, s_en = 0.0, s_m = 0.0;
+
+  for (int t = 0; t < T; ++t) {
+    const long bt = (long)b * T + t;
+    StepIn<C> in;
+    load_step<C>(a, bt, in);
+    float eps[N];
+    load_row<N>(a.eps + bt * N, eps);
+    ElboStep<C> es;
+    ok = elbo_sample_t<C>(a, g, tiles + TL::oX0, tiles + TL::oV, bt, jitter, eps, es) && ok;
+
+    // entropy = -log N(z; mu_s, Ls Ls^T) = 1/2 |eps|^2 + sum log Ls_ii + n/2 log 2pi            (:389)
+    float e2 = 0.f;
+    KV_UNROLL for (int j = 0; j < N; ++j) e2 = fmaf(eps[j], eps[j], e2);
+    s_en += (double)(0.5f * e2 + logdet_half<C>(g, es.dg) + 0.5f * N * KV_LOG2PI);
+
+    if (t == 0) {
+      // log N(z_0; mu0, Sigma0)                                                                 (:380-381)
+      float S0[R][N], L0[R][N], invd0[N], dg0[R];
+      copy_rows<C, N>(base + Base<C>::oS0, row0, S0);
+      ok = chol_dist<L, R>(g, S0, L0, invd0, dg0) && ok;
+      auto L0_v = publish<MEM, L, R, N>(g, L0, tiles + TL::oX1);
+      float w[N];
+      KV_UNROLL for (int j = 0; j < N; ++j) w[j] = es.z[j] - base[Base<C>::oMu0 + j];
+      solve_vec_l<N>(w, L0_v, invd0);
+      float q = 0.f;
+      KV_UNROLL for (int j = 0; j < N; ++j) q = fmaf(w[j], w[j], q);
+      s_in += (double)(-0.5f * (N * KV_LOG2PI + q) - logdet_half<C>(g, dg0));
+    } else {
+      // log N(z_t - A_t z_{t-1} - B_t u_t; 0, sym(Q_t)+jI)                                      (:353-369)
+      float A[R][N], Bm[R][M];
+      mix_A<C>(base, in.al, row0, A);
+      mix_B<C>(base, in.al, row0, Bm);
+      float x_own[R], x[N];
+      KV_UNROLL for (int r = 0; r < R; ++r) {
+        float s1 = 0.f, s2 = 0.f;
+        KV_UNROLL for (int j = 0; j < N; ++j) s1 = fmaf(A[r][j], zprev[j], s1);
+        KV_UNROLL for (int j = 0; j < M; ++j) s2 = fmaf(Bm[r][j], in.u[j], s2);
+        x_own[r] = es.z_own[r] - (s1 + s2);
+      }
+      allgather<MEM, L, R>(g, x_own, tiles + TL::oV2, x);
+      float q = 0.f, ld;
+      if constexpr (C::QPM) {
+        float Q[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
+        mix_Q<C>(base, in.al, row0, Q);
+        sym_jitter_rows<C>(g, Q, tiles + TL::oX1, jitter, Qs);
+        ok = chol_dist<L, R>(g, Qs, LQ, invdQ, dgQ) && ok;
+        auto LQ_v = publish<MEM, L, R, N>(g, LQ, tiles + TL::oX2);
+        solve_vec_l<N>(x, LQ_v, invdQ);
+        ld = logdet_half<C>(g, dgQ);
+      } else {
+        solve_vec_l<N>(x, LQc_v, ec.invdQ);
+        ld = ec.logdetQ;
+      }
+      KV_UNROLL for (int j = 0; j < N; ++j) q = fmaf(x[j], x[j], q);
+      s_tr += (double)(-0.5f * (N * KV_LOG2PI + q) - ld);
+    }
+    {
+      // mask_t * log N(y_t - C_t z_t; 0, R)                                                     (:372-377)
+      float Ct[R][P];
+      mix_Ct<C>(base, in.al, row0, Ct);
+      float e[P];
+      KV_UNROLL for (int q = 0; q < P; ++q) {
+        float s = 0.f;
+        KV_UNROLL for (int r = 0; r < R; ++r) s = fmaf(Ct[r][q], es.z_own[r], s);
+        e[q] = s;
+      }
+      g.allreduce(e);
+      KV_UNROLL for (int q = 0; q < P; ++q) e[q] = in.y[q] - e[q];
+      RegView<P, P> LR_v{ec.LR};
+      solve_vec_l<P>(e, LR_v, ec.invdR);
+      float q2 = 0.f;
+      KV_UNROLL for (int q = 0; q < P; ++q) q2 = fmaf(e[q], e[q], q2);
+      s_em += (double)((-0.5f * (P * KV_LOG2PI + q2) - ec.logdetR) * in.m);
+      s_m += (double)in.m;
+    }
+    KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = es.z[j];
+  }
+  if (active && g.lane == 0) {
+    acc[0] += s_tr; acc[1] += s_em; acc[2] += s_in; acc[3] += s_en; acc[4] += s_m;
+  }
+  if (!ok && active) *a.info = 1;
+}
+
+}  // namespace kvae

@@ -73,10 +73,12 @@ template <class C> struct Tiles {
   static constexpr int oX0 = 0;
   static constexpr int oX1 = oX0 + szNN;
   static constexpr int oX2 = oX1 + szNN;
-  static constexpr int oC = oX2 + szNN;
+  static constexpr int oXP = oX2 + szNN;  // persistent tile (e.g. chol of a constant Q)
+  static constexpr int oC = oXP + szNN;
   static constexpr int oK = oC + szNP;
-  static constexpr int oV = oK + szNP;   // vector all-gather slot (N floats)
-  static constexpr int total = C::MEM ? (oV + pad4(C::N)) : 0;
+  static constexpr int oV = oK + szNP;   // vector all-gather slots (N floats each)
+  static constexpr int oV2 = oV + pad4(C::N);
+  static constexpr int total = C::MEM ? (oV2 + pad4(C::N)) : 0;
 };
 
 // ---------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 // memory; per-group publish tiles behind them.
 #pragma once
 #include <cuda_runtime.h>
-#include "kvae_fwd.cuh"
+#include "kvae_bwd.cuh"
 
 namespace kvae {
 
@@ -50,6 +50,190 @@ template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth,
   }
   const int grid = (a.B + GPB - 1) / GPB;
   k_filter_smooth<C><<<grid, kThreads, sm, s>>>(a, bp, smooth);
+  return (int)cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// ELBO: per-CTA partial sums (double) -> one-block final reduction
+// ------------------------------------------------------------------------------------------------
+template <class C> constexpr size_t smem_bytes_elbo() { return smem_bytes<C>(); }
+
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float jitter, double* __restrict__ partials) {
+  extern __shared__ f4 smem_raw[];
+  float* base = reinterpret_cast<float*>(smem_raw);
+  float* tiles_all = stage_base<C>(base, bp);
+  constexpr int GPB = kThreads / C::L;
+  const int gi = threadIdx.x / C::L;
+  Group<C::L, C::R> g{(int)(threadIdx.x % C::L)};
+  int b = blockIdx.x * GPB + gi;
+  const bool active = b < a.B;
+  if (!active) b = a.B - 1;
+  float* tiles = tiles_all + gi * Tiles<C>::total;
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  elbo_sweep<C>(a, base, tiles, g, b, active, jitter, acc);
+  // block reduction (fixed order -> deterministic)
+  __shared__ double red[kThreads / 32][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < kThreads / 32; ++wq) v += red[wq][threadIdx.x];
+    partials[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
+  }
+}
+
+// terms: [0] trans [1] emiss [2] init [3] entropy [4] sum(mask) [5] elbo [6] 1/max(sum mask,1) [7] 0
+static __global__ void k_elbo_final(const double* __restrict__ partials, int nblocks, float* __restrict__ terms) {
+  __shared__ double red[256][5];
+  double v[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+    for (int j = 0; j < 5; ++j) v[j] += partials[(size_t)i * 5 + j];
+  for (int j = 0; j < 5; ++j) red[threadIdx.x][j] = v[j];
+  __syncthreads();
+  for (int s = blockDim.x / 2; s >= 1; s >>= 1) {
+    if ((int)threadIdx.x < s) for (int j = 0; j < 5; ++j) red[threadIdx.x][j] += red[threadIdx.x + s][j];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = red[0][4] < 1.0 ? 1.0 : red[0][4];
+    for (int j = 0; j < 5; ++j) terms[j] = (float)red[0][j];
+    terms[5] = (float)((red[0][0] + red[0][1] + red[0][2] + red[0][3]) / n);
+    terms[6] = (float)(1.0 / n);
+    terms[7] = 0.f;
+  }
+}
+
+template <class C> size_t elbo_ws_bytes(int B) {
+  constexpr int GPB = kThreads / C::L;
+  return sizeof(double) * 5 * (size_t)((B + GPB - 1) / GPB);
+}
+
+template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitter, float* terms, void* ws, cudaStream_t s) {
+  constexpr int GPB = kThreads / C::L;
+  const size_t sm = smem_bytes_elbo<C>();
+  static bool attr_set = false;
+  if (sm > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_elbo<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = (a.B + GPB - 1) / GPB;
+  k_elbo<C><<<grid, kThreads, sm, s>>>(a, bp, jitter, reinterpret_cast<double*>(ws));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  k_elbo_final<<<1, 256, 0, s>>>(reinterpret_cast<const double*>(ws), grid, terms);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: sweeps 3 + 4 per group, parameter gradients reduced per CTA (fixed order), then a
+// second kernel sums the per-CTA partials.
+// ------------------------------------------------------------------------------------------------
+struct GradPtrs { float *dA, *dB, *dC, *dQ; };
+
+template <class C> constexpr size_t smem_floats_bwd() {
+  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(kThreads / C::L) * BTiles<C>::total;
+  constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
+  return tiles > red ? tiles : red;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
+                                                  const float* __restrict__ terms, float* __restrict__ partials) {
+  extern __shared__ f4 smem_raw[];
+  float* base = reinterpret_cast<float*>(smem_raw);
+  float* tiles_all = stage_base<C>(base, bp);
+  constexpr int GPB = kThreads / C::L;
+  const int gi = threadIdx.x / C::L;
+  Group<C::L, C::R> g{(int)(threadIdx.x % C::L)};
+  int b = blockIdx.x * GPB + gi;
+  const bool active = b < a.B;
+  if (!active) b = a.B - 1;
+  float* tiles = tiles_all + gi * BTiles<C>::total;
+  w.c_elbo = g_elbo ? (*g_elbo) * terms[6] : 0.f;
+  GradAcc<C> acc;
+  acc.zero();
+  bwd_sweep3<C>(a, w, base, tiles, g, b, active, acc);
+  bwd_sweep4<C>(a, w, base, tiles, g, b, active, acc);
+  if (!active) acc.zero();
+  // reduce over the groups of a warp (xor over the group-index bits of the lane id)
+#pragma unroll
+  for (int off = C::L; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
+  }
+  // then over the warps of the CTA in fixed order, through shared memory (tiles are dead now)
+  float* red = tiles_all;
+  __syncthreads();
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int wq = 0; wq < kThreads / 32; ++wq) {
+    if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) partials[(size_t)blockIdx.x * GradAcc<C>::PSZ + i] = red[i];
+}
+
+// sums the per-CTA partials (double accumulation) and scatters into dA | dB | dC | dQ
+static __global__ void k_param_final(const float* __restrict__ partials, int nblocks, int psz, int nA, int nB, int nC,
+                              GradPtrs gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= psz) return;
+  double v = 0.0;
+  for (int blk = 0; blk < nblocks; ++blk) v += (double)partials[(size_t)blk * psz + i];
+  const float f = (float)v;
+  if (i < nA) gp.dA[i] = f;
+  else if (i < nA + nB) gp.dB[i - nA] = f;
+  else if (i < nA + nB + nC) gp.dC[i - nA - nB] = f;
+  else if (gp.dQ) gp.dQ[i - nA - nB - nC] = f;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <class C> size_t bwd_ws_bytes(int B, int T) {
+  constexpr int GPB = kThreads / C::L;
+  const size_t nn = align256(sizeof(float) * (size_t)B * T * C::N * C::N);
+  const size_t nv = align256(sizeof(float) * (size_t)B * T * C::N);
+  const size_t np = align256(sizeof(float) * (size_t)((B + GPB - 1) / GPB) * GradAcc<C>::PSZ);
+  return 2 * nn + 2 * nv + np;
+}
+
+template <class C>
+int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo, const float* terms, void* ws,
+               GradPtrs gp, cudaStream_t s) {
+  constexpr int GPB = kThreads / C::L;
+  const size_t sm = sizeof(float) * smem_floats_bwd<C>();
+  static bool attr_set = false;
+  if (sm > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const size_t nn = align256(sizeof(float) * (size_t)a.B * a.T * C::N * C::N);
+  const size_t nv = align256(sizeof(float) * (size_t)a.B * a.T * C::N);
+  char* p = reinterpret_cast<char*>(ws);
+  w.w_Sig_f = reinterpret_cast<float*>(p); p += nn;
+  w.w_Sig_p = reinterpret_cast<float*>(p); p += nn;
+  w.w_mu_f = reinterpret_cast<float*>(p); p += nv;
+  w.w_mu_p = reinterpret_cast<float*>(p); p += nv;
+  float* partials = reinterpret_cast<float*>(p);
+  const int grid = (a.B + GPB - 1) / GPB;
+  k_bwd<C><<<grid, kThreads, sm, s>>>(a, w, bp, g_elbo, terms, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  constexpr int psz = GradAcc<C>::PSZ;
+  k_param_final<<<(psz + 127) / 128, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
+                                                  C::K * C::P * C::N, gp);
   return (int)cudaGetLastError();
 }
 

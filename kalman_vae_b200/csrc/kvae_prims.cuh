@@ -248,9 +248,11 @@ template <int D> KV_FN bool chol_small(const float (&a)[D][D], float (&l)[D][D],
 // a (lower triangle read) and of l.  invd (1/diag) is replicated.  Column j is finished by
 // broadcasting the pivot row from its owner lane with warp shuffles.
 template <int L, int R>
-KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l)[R][L * R], float (&invd)[L * R]) {
+KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l)[R][L * R], float (&invd)[L * R],
+                     float (&dg_own)[R]) {
   constexpr int N = L * R;
   bool ok = true;
+  KV_UNROLL for (int r = 0; r < R; ++r) dg_own[r] = 1.0f;
   KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) l[r][j] = 0.f;
   KV_UNROLL for (int j = 0; j < N; ++j) {
     const int owner = j / R, jr = j % R;
@@ -267,6 +269,7 @@ KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l
       KV_UNROLL for (int q = 0; q < j; ++q) v = fmaf(-l[r][q], lj[q], v);
       v *= invd[j];
       l[r][j] = (i > j) ? v : ((i == j) ? d : 0.f);
+      if (i == j) dg_own[r] = d;
     }
   }
   return ok;
@@ -377,18 +380,9 @@ KV_FN void solve_rows_lu(float (&x)[R][D], const V& LU, const float (&invu)[D]) 
     }
   }
 }
-// x := x (LU)^-T for each local row  (x A^T = b  ->  y U^T = b, x L^T = y; dot form with row j)
+// x := x (LU)^-T for each local row  (x U^T L^T = b  ->  y L^T = b, then x U^T = y; dot form with row j)
 template <int R, int D, class V>
 KV_FN void solve_rows_lut(float (&x)[R][D], const V& LU, const float (&invu)[D]) {
-  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
-    float uj[D];
-    LU.row(j, uj);
-    KV_UNROLL for (int r = 0; r < R; ++r) {
-      float s = x[r][j];
-      KV_UNROLL for (int q = j + 1; q < D; ++q) s = fmaf(-x[r][q], uj[q], s);
-      x[r][j] = s * invu[j];
-    }
-  }
   KV_UNROLL for (int j = 1; j < D; ++j) {
     float lj[D];
     LU.row(j, lj);
@@ -396,6 +390,15 @@ KV_FN void solve_rows_lut(float (&x)[R][D], const V& LU, const float (&invu)[D])
       float s = x[r][j];
       KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-x[r][q], lj[q], s);
       x[r][j] = s;
+    }
+  }
+  KV_UNROLL for (int j = D - 1; j >= 0; --j) {
+    float uj[D];
+    LU.row(j, uj);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      float s = x[r][j];
+      KV_UNROLL for (int q = j + 1; q < D; ++q) s = fmaf(-x[r][q], uj[q], s);
+      x[r][j] = s * invu[j];
     }
   }
 }

@@ -55,13 +55,73 @@ int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const k
   return -3;
 }
 
-template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims&) { return 0; }
+template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims& d) {
+#define X(l) \
+  if (d.lanes == (l)) { if constexpr (N % (l) == 0) return elbo_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B); }
+  KV_FOR_EACH_L(X)
+#undef X
+  return 0;
+}
+
 template <>
-int ShapeOps<N, P, M, K>::elbo(const kvae_dims&, const kvae_inputs&, const kvae_states&, const float*, float, float*,
-                               void*, int32_t*, cudaStream_t) { return -4; }
-template <> size_t ShapeOps<N, P, M, K>::bwd_ws(const kvae_dims&) { return 0; }
+int ShapeOps<N, P, M, K>::elbo(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const float* eps,
+                               float jitter, float* terms, void* ws, int32_t* info, cudaStream_t s) {
+  Args a = make_args(d, in, st, info);
+  a.eps = eps;
+  const BasePtrs bp = make_base(in);
+  const bool sw = d.q_per_mode != 0;
+#define X(l)                                                                                     \
+  if (d.lanes == (l)) {                                                                          \
+    if constexpr (N % (l) == 0) {                                                                \
+      return sw ? launch_elbo<Cfg<N, P, M, K, (l), true, true>>(a, bp, jitter, terms, ws, s)     \
+                : launch_elbo<Cfg<N, P, M, K, (l), false, false>>(a, bp, jitter, terms, ws, s);  \
+    }                                                                                            \
+  }
+  KV_FOR_EACH_L(X)
+#undef X
+  return -3;
+}
+
+template <> size_t ShapeOps<N, P, M, K>::bwd_ws(const kvae_dims& d) {
+  const bool sw = d.q_per_mode != 0;
+#define X(l)                                                                                     \
+  if (d.lanes == (l)) {                                                                          \
+    if constexpr (N % (l) == 0) {                                                                \
+      return sw ? bwd_ws_bytes<Cfg<N, P, M, K, (l), true, true>>(d.B, d.T)                       \
+                : bwd_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B, d.T);                    \
+    }                                                                                            \
+  }
+  KV_FOR_EACH_L(X)
+#undef X
+  return 0;
+}
+
 template <>
-int ShapeOps<N, P, M, K>::bwd(const kvae_dims&, const kvae_inputs&, const kvae_states&, const BwdExtra&, int32_t*,
-                              cudaStream_t) { return -4; }
+int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const BwdExtra& x,
+                              int32_t* info, cudaStream_t s) {
+  Args a = make_args(d, in, st, info);
+  a.eps = x.eps;
+  const BasePtrs bp = make_base(in);
+  BwdArgs w{};
+  if (x.cot) {
+    w.c_mu_s = x.cot->mus_smooth; w.c_Sig_s = x.cot->Sigmas_smooth; w.c_mu_f = x.cot->mus_filt;
+    w.c_Sig_f = x.cot->Sigmas_filt; w.c_mu_p = x.cot->mus_pred; w.c_Sig_p = x.cot->Sigmas_pred;
+    w.c_A = x.cot->A_list; w.c_B = x.cot->B_list; w.c_C = x.cot->C_list;
+  }
+  w.dY = x.grads->dY; w.dU = x.grads->dU; w.dalpha = x.grads->dalpha;
+  w.jitter = x.jitter;
+  GradPtrs gp{x.grads->dA, x.grads->dBm, x.grads->dC, x.grads->dQ};
+  const bool sw = d.q_per_mode != 0;
+#define X(l)                                                                                             \
+  if (d.lanes == (l)) {                                                                                  \
+    if constexpr (N % (l) == 0) {                                                                        \
+      return sw ? launch_bwd<Cfg<N, P, M, K, (l), true, true>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s)    \
+                : launch_bwd<Cfg<N, P, M, K, (l), false, false>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s); \
+    }                                                                                                    \
+  }
+  KV_FOR_EACH_L(X)
+#undef X
+  return -3;
+}
 
 }  // namespace kvae

@@ -1,0 +1,178 @@
+"""Host-side mirrors of the reference's dynamics-parameter modules.
+
+They keep the reference's constructor signatures, parameter / sub-module names (so state dicts
+load unchanged: `A,B,C[,Q]`, `lstm.*`, `head_w.*`, `markov_regime_posterior.{bigru,linear_head,
+init_head}.*`) and the protocol `KalmanFilter` relies on (`is_switching_dynamics`, `reset_state`,
+`state_seq`, `Q_seq`, `elbo_terms`, `compute_step`, `compute_batch`), and add one method the CUDA
+path uses: `compute_weights(...) -> alpha [B,T,K]`.  The mixing of the K base matrices by alpha
+(dyn_param.py:58-60, switch_dyn_param.py:82-86) is NOT done here: it happens inside the kernels.
+
+The recurrent networks themselves (LSTM / bi-GRU, cuDNN) stay in PyTorch: they are out of the
+hot path's scope.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch.nn.functional import gumbel_softmax
+
+
+class DynamicsParameter(nn.Module):
+    """Mirror of kvae/kalman/dyn_param.py:5-63 (LSTM 'dynamics parameter network')."""
+
+    def __init__(self, A, B, C, hidden_lstm=50):
+        super().__init__()
+        self.is_switching_dynamics = False
+        self.K = A.size(0)
+        self.n, self.m, self.p = A.size(1), B.size(2), C.size(1)
+        self.A = nn.Parameter(A.clone())
+        self.B = nn.Parameter(B.clone())
+        self.C = nn.Parameter(C.clone())
+        self.lstm_state = None
+        self.state_seq = None
+        if self.K > 1:
+            self.lstm = nn.LSTM(input_size=self.p, hidden_size=hidden_lstm, num_layers=1, batch_first=True)
+            self.head_w = nn.Linear(hidden_lstm, self.K)
+            with torch.no_grad():  # bias alpha towards mode 0 at initialisation (dyn_param.py:31-33)
+                self.head_w.bias.fill_(-10.0)
+                self.head_w.bias[0] = 0.0
+
+    def reset_state(self):
+        self.lstm_state = None
+        self.state_seq = []
+
+    def step_weights(self, a_tprev):
+        """alpha_t [B,K] from the previous (observed or predicted) encoding; advances the LSTM."""
+        batch = a_tprev.size(0)
+        if self.K == 1:
+            w = torch.ones(batch, 1, device=a_tprev.device, dtype=a_tprev.dtype)
+        else:
+            h, self.lstm_state = self.lstm(a_tprev.unsqueeze(1), self.lstm_state)
+            w = torch.softmax(self.head_w(h.squeeze(1)), dim=-1)
+        self.state_seq.append(w)
+        return w
+
+    def compute_step(self, a_tprev):
+        """Reference protocol (dyn_param.py:39-63): returns the mixed (A,B,C) for one step."""
+        w = self.step_weights(a_tprev)
+        A = torch.einsum("bk,kij->bij", w, self.A)
+        B = torch.einsum("bk,knm->bnm", w, self.B)
+        C = torch.einsum("bk,kpn->bpn", w, self.C)
+        return A, B, C
+
+    def compute_weights(self, a_seq):
+        """alpha [B,T,K] for a fully observed sequence in ONE recurrent call.
+
+        With mask == 1 the filter feeds the network y_for_dyn = a_{t-1} exactly
+        (kalman_filter.py:142,183-185), i.e. the input sequence [0, a_0, ..., a_{T-2}]; running the
+        LSTM once over it equals the reference's T single-step calls.
+        """
+        batch, T, _ = a_seq.shape
+        if self.K == 1:
+            alpha = torch.ones(batch, T, 1, device=a_seq.device, dtype=a_seq.dtype)
+        else:
+            shifted = torch.cat([torch.zeros_like(a_seq[:, :1]), a_seq[:, :-1]], dim=1)
+            h, self.lstm_state = self.lstm(shifted, self.lstm_state)
+            alpha = torch.softmax(self.head_w(h), dim=-1)
+        self.state_seq = alpha  # what the reference leaves after filter() (kalman_filter.py:188-191)
+        return alpha
+
+
+class StickyRegimePrior:
+    """Mirror of switch_dyn_param.py:98-110."""
+
+    def __init__(self, K, p_stay=0.9):
+        self.K = K
+        self.p_stay = p_stay
+        self.transition_matrix = torch.ones((K, K)) * ((1 - p_stay) / (K - 1))
+        self.transition_matrix.fill_diagonal_(p_stay)
+
+
+class MarkovVariationalRegimePosterior(nn.Module):
+    """Mirror of switch_dyn_param.py:113-129 (bi-GRU + transition / initial heads)."""
+
+    def __init__(self, K, input_dim, hidden_size=32):
+        super().__init__()
+        self.K = K
+        self.hidden_size = hidden_size
+        self.bigru = nn.GRU(input_size=input_dim, hidden_size=hidden_size, num_layers=1, batch_first=True,
+                            bidirectional=True)
+        self.linear_head = nn.Linear(2 * hidden_size, K * K)
+        self.init_head = nn.Linear(2 * hidden_size, K)
+
+    def forward(self, a_seq):
+        h_seq, _ = self.bigru(a_seq)
+        logits = self.linear_head(h_seq)
+        B, T, _ = logits.shape
+        return logits.view(B, T, self.K, self.K), self.init_head(h_seq[:, 0])
+
+
+class SwitchingDynamicsParameter(nn.Module):
+    """Mirror of kvae/kalman/switch_dyn_param.py:7-95 (SKVAE regime posterior)."""
+
+    def __init__(self, A, B, C, Q=None, prior=None, hidden_lstm=32, markov_regime_posterior=None):
+        super().__init__()
+        self.is_switching_dynamics = True
+        self.K = A.size(0)
+        self.n, self.m, self.p = A.size(1), B.size(2), C.size(1)
+        self.tau = 0.5
+        if Q is None:
+            Q = torch.eye(self.n, device=A.device, dtype=A.dtype).unsqueeze(0).repeat(self.K, 1, 1)
+        self.A = nn.Parameter(A.clone())
+        self.B = nn.Parameter(B.clone())
+        self.C = nn.Parameter(C.clone())
+        self.Q = nn.Parameter(Q.clone())
+        self.s_tprev = None
+        self.prior = prior if prior is not None else StickyRegimePrior(self.K)
+        self.markov_regime_posterior = markov_regime_posterior or MarkovVariationalRegimePosterior(
+            self.K, input_dim=self.p, hidden_size=hidden_lstm)
+        self.hidden_size = hidden_lstm
+        self.state_seq = None
+        self.Q_seq = None
+
+    def reset_state(self):
+        self.state_seq = None
+
+    def compute_weights(self, a_seq, is_training=True):
+        """Regime weights y_seq [B,T,K] plus the log q / log p bookkeeping of
+        switch_dyn_param.py:51-79; no mixed matrices are materialised."""
+        batch, T, _ = a_seq.size()
+        dev, dt = a_seq.device, a_seq.dtype
+        if self.K == 1:
+            self.log_qseq = torch.zeros(batch, T, device=dev, dtype=dt)
+            self.log_pseq = torch.zeros(batch, T, device=dev, dtype=dt)
+            self.state_seq = torch.ones(batch, T, 1, device=dev, dtype=dt)
+            return self.state_seq
+        logits, init_logits = self.markov_regime_posterior(a_seq)
+        y0 = gumbel_softmax(init_logits, tau=self.tau, hard=not is_training, dim=-1)
+        log_q0 = torch.log_softmax(init_logits, dim=-1)
+        log_p0 = torch.full_like(log_q0, 1.0 / self.K).log()
+        ys, lq, lp = [y0], [(y0 * log_q0).sum(-1)], [(y0 * log_p0).sum(-1)]
+        trans = self.prior.transition_matrix.to(device=dev, dtype=dt)
+        y_prev = y0
+        for t in range(1, T):
+            l_t = torch.matmul(y_prev.unsqueeze(1), logits[:, t]).squeeze(1)
+            y_t = gumbel_softmax(l_t, tau=self.tau, hard=not is_training, dim=-1)
+            lq.append((y_t * torch.log_softmax(l_t, dim=-1)).sum(-1))
+            tp = torch.matmul(y_prev.unsqueeze(1), trans).squeeze(1)
+            lp.append((y_t * torch.log(tp.clamp_min(1e-8))).sum(-1))
+            ys.append(y_t)
+            y_prev = y_t
+        self.state_seq = torch.stack(ys, 1)
+        self.log_qseq = torch.stack(lq, 1)
+        self.log_pseq = torch.stack(lp, 1)
+        return self.state_seq
+
+    def compute_batch(self, a_seq, is_training=True):
+        """Reference protocol (switch_dyn_param.py:37-92): mixed sequences for callers that want them."""
+        y_seq = self.compute_weights(a_seq, is_training)
+        batch, T, _ = a_seq.size()
+        A_seq = torch.einsum("btk,kij->btij", y_seq, self.A)
+        B_seq = torch.einsum("btk,knm->btnm", y_seq, self.B)
+        Q_seq = torch.einsum("btk,kij->btij", y_seq, self.Q)
+        C_seq = self.C[0].expand(batch, T, -1, -1)
+        self.Q_seq = Q_seq
+        return A_seq, B_seq, C_seq, Q_seq
+
+    def elbo_terms(self):
+        return self.log_qseq, self.log_pseq

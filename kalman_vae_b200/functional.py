@@ -1,0 +1,211 @@
+"""Autograd plumbing over the C ABI: forward recursion, ELBO and the explicit adjoint.
+
+Three entry points:
+  smooth_fwd(...)            filter (+ RTS smoother) -> the reference's 7-/9-tuple tensors
+  SmoothFunction             autograd node for dense cotangents of those outputs (general path)
+  FusedElboFunction          elbo as a function of the ORIGINAL inputs (Y,U,alpha,A,B,C,Q): its
+                             backward runs the complete adjoint (ELBO + smoother + filter + mixing)
+                             in one launch, with the states saved by smooth_fwd re-used as is.
+
+torch is used for memory, streams and autograd bookkeeping only; all arithmetic of the path is in
+libkvae_kalman.so.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import capi
+
+
+@dataclass
+class Problem:
+    """Inputs of one call, normalised to contiguous fp32 CUDA tensors."""
+    Y: torch.Tensor
+    U: Optional[torch.Tensor]
+    mask: Optional[torch.Tensor]
+    alpha: torch.Tensor
+    A: torch.Tensor
+    Bm: torch.Tensor
+    C: torch.Tensor
+    Q: torch.Tensor
+    R: torch.Tensor
+    mu0: torch.Tensor
+    Sigma0: torch.Tensor
+    q_per_mode: bool
+    c_shared: bool
+    lanes: int = 0
+    mu_init: Optional[torch.Tensor] = None
+    Sigma_init: Optional[torch.Tensor] = None
+    dims: object = field(default=None, repr=False)
+
+    def __post_init__(self):
+        B, T, p = self.Y.shape
+        K, n, m = self.Bm.shape
+        self.dims = capi.make_dims(B, T, n, p, m, K, self.q_per_mode, self.c_shared, self.lanes)
+        if not capi.supported(self.dims):
+            raise capi.KvaeError(
+                f"shape (n={n}, p={p}, m={m}, K={K}, switching={self.q_per_mode}, lanes={self.lanes}) is not "
+                "instantiated in libkvae_kalman.so; add it to kalman_vae_b200/csrc/kvae_configs.h and rebuild")
+
+    @property
+    def shape(self):
+        d = self.dims
+        return d.B, d.T, d.n, d.p, d.m, d.K
+
+    def inputs(self, Y=None, U=None):
+        return capi.make_inputs(self.Y if Y is None else Y, self.U if U is None else U, self.mask, self.alpha,
+                                self.A, self.Bm, self.C, self.Q, self.R, self.mu0, self.Sigma0,
+                                self.mu_init, self.Sigma_init)
+
+
+def prep(t, device=None):
+    """contiguous fp32 CUDA tensor with a 16-byte aligned base (no copy when already so)."""
+    if t is None:
+        return None
+    t = t.detach()
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+_info_cache = {}
+
+
+def info_word(device):
+    """One persistent int32 flag per device (zeroed by the caller when it wants to read it)."""
+    w = _info_cache.get(device)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=device)
+        _info_cache[device] = w
+    return w
+
+
+@dataclass
+class States:
+    mus_filt: torch.Tensor
+    Sigmas_filt: torch.Tensor
+    mus_pred: torch.Tensor
+    Sigmas_pred: torch.Tensor
+    mus_smooth: Optional[torch.Tensor] = None
+    Sigmas_smooth: Optional[torch.Tensor] = None
+
+    def c_struct(self):
+        return capi.make_states(self.mus_filt, self.Sigmas_filt, self.mus_pred, self.Sigmas_pred,
+                                self.mus_smooth, self.Sigmas_smooth)
+
+
+def smooth_fwd(pb: Problem, smooth=True, lists=True):
+    """Runs the forward recursion; returns (States, A_list, B_list, C_list)."""
+    B, T, n, p, m, K = pb.shape
+    dev = pb.Y.device
+    e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    st = States(e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n),
+                e(B, T, n, 1) if smooth else None, e(B, T, n, n) if smooth else None)
+    A_list = e(B, T, n, n) if lists else None
+    B_list = e(B, T, n, m) if lists else None
+    # shared emission matrix: the reference returns a stack of C[0] (switch_dyn_param.py:85-86);
+    # an expanded view has the same values without B*T copies of it
+    C_list = None
+    if lists and not pb.c_shared:
+        C_list = e(B, T, p, n)
+    capi.filter_smooth_fwd(pb.dims, pb.inputs(), st.c_struct(), A_list, B_list, C_list, info_word(dev), dev)
+    if lists and pb.c_shared:
+        C_list = pb.C[0].expand(B, T, p, n)
+    return st, A_list, B_list, C_list
+
+
+def elbo_terms(pb: Problem, st: States, eps, jitter=1e-6, Y=None, U=None):
+    """terms[8] (see include/kvae_kalman.h)."""
+    dev = pb.Y.device
+    terms = torch.empty(8, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(capi.elbo_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
+    capi.elbo_fwd(pb.dims, pb.inputs(Y, U), st.c_struct(), eps, jitter, terms, ws, info_word(dev), dev)
+    return terms
+
+
+def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=None, cot=None, need_dU=True,
+            Y_elbo=None, U_elbo=None):
+    """Explicit adjoint.  Returns dict(dY,dU,dalpha,dA,dBm,dC,dQ[,dY_elbo,dU_elbo])."""
+    B, T, n, p, m, K = pb.shape
+    dev = pb.Y.device
+    e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    grads = dict(dY=e(B, T, p), dU=e(B, T, m) if need_dU else None, dalpha=e(B, T, K),
+                 dA=e(K, n, n), dBm=e(K, n, m), dC=e(K, p, n), dQ=e(K, n, n) if pb.q_per_mode else None)
+    ws = torch.empty(max(capi.bwd_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
+    capi.bwd(pb.dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
+    return grads
+
+
+_COT_ORDER = ("mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
+              "A_list", "B_list", "C_list")
+
+
+class SmoothFunction(torch.autograd.Function):
+    """(Y, U, alpha, A, Bm, C, Q) -> the outputs of filter()/smooth(); dense-cotangent backward."""
+
+    @staticmethod
+    def forward(ctx, pb: Problem, smooth: bool, Y, U, alpha, A, Bm, C, Q):
+        st, A_list, B_list, C_list = smooth_fwd(pb, smooth=smooth, lists=True)
+        ctx.pb, ctx.st, ctx.smooth = pb, st, smooth
+        ctx.has_U = U is not None
+        outs = [st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred, A_list, B_list]
+        ctx.c_materialised = not pb.c_shared
+        if ctx.c_materialised:
+            outs.append(C_list)
+        if smooth:
+            outs = [st.mus_smooth, st.Sigmas_smooth] + outs
+        ctx.mark_non_differentiable()
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        pb, st = ctx.pb, ctx.st
+        gouts = list(gouts)
+        names = (["mus_smooth", "Sigmas_smooth"] if ctx.smooth else []) + \
+                ["mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "A_list", "B_list"] + \
+                (["C_list"] if ctx.c_materialised else [])
+        cot = {k: prep(g) for k, g in zip(names, gouts) if g is not None}
+        st_b = st
+        if not ctx.smooth:
+            # filter-only call: the adjoint kernel still wants smoothed-state buffers; with no
+            # cotangent on them and T handled generically they are only read for D = Ss1 - Sp1
+            # whose adjoint is multiplied by zero, so alias the filtered ones.
+            st_b = States(st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred, st.mus_filt, st.Sigmas_filt)
+        g = adjoint(pb, st_b, cot=cot, need_dU=ctx.has_U)
+        return (None, None, g["dY"], g["dU"] if ctx.has_U else None, g["dalpha"], g["dA"], g["dBm"], g["dC"],
+                g["dQ"] if pb.q_per_mode else None)
+
+
+class FusedElboFunction(torch.autograd.Function):
+    """elbo(Y, U, alpha, A, Bm, C, Q) with the smoothed states of a previous smooth_fwd on the same
+    inputs passed as constants.  forward: ELBO sweep; backward: sweeps 3+4 in one launch."""
+
+    @staticmethod
+    def forward(ctx, pb: Problem, st: States, eps, jitter, extra, Y, U, alpha, A, Bm, C, Q):
+        terms = elbo_terms(pb, st, eps, jitter)
+        ctx.pb, ctx.st, ctx.eps, ctx.jitter, ctx.terms = pb, st, eps, jitter, terms
+        ctx.has_U = U is not None
+        # extra: optional 0-dim tensor added inside the normalisation: (log_p - log_q).sum()
+        val = terms[5]
+        if extra is not None:
+            val = val + extra * terms[6]
+        ctx.has_extra = extra is not None
+        return val.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        pb = ctx.pb
+        g = g.detach().to(torch.float32).reshape(1).contiguous()
+        gr = adjoint(pb, ctx.st, eps=ctx.eps, jitter=ctx.jitter, g_elbo=g, terms=ctx.terms, need_dU=ctx.has_U)
+        g_extra = (g * ctx.terms[6]).reshape(()) if ctx.has_extra else None
+        return (None, None, None, None, g_extra, gr["dY"], gr["dU"] if ctx.has_U else None, gr["dalpha"], gr["dA"],
+                gr["dBm"], gr["dC"], gr["dQ"] if pb.q_per_mode else None)

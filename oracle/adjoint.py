@@ -109,6 +109,8 @@ def smooth_elbo_backward(case, saved, g_elbo=1.0, cot=None, dtype=torch.float64,
         A_b[:, t + 1] += Wb.mT @ Sf[:, t]
     Sf_b[:, T - 1] += Ss_b[:, T - 1]
     mf_b[:, T - 1] += ms_b[:, T - 1]
+    dbg = dict(Sf_b=Sf_b.clone(), Sp_b=Sp_b.clone(), mf_b=mf_b.clone().squeeze(-1), mp_b=mp_b.clone().squeeze(-1),
+               A_b3=A_b.clone(), C_b3=C_b.clone(), Q_b3=Q_b.clone())
 
     # ------------------------------------------------------------------ A.5 filter adjoint (t = T-1 .. 0)
     for t in range(T - 1, -1, -1):
@@ -165,4 +167,5 @@ def smooth_elbo_backward(case, saved, g_elbo=1.0, cot=None, dtype=torch.float64,
         dalpha = dalpha + torch.einsum("btij,kij->btk", Q_b, Qk)
         out["dQ"] = torch.einsum("btk,btij->kij", alpha, Q_b)
     out["dalpha"] = dalpha
+    out["_dbg"] = dbg
     return out

@@ -5,6 +5,8 @@
 #include <cstring>
 #include "../../kalman_vae_b200/csrc/kvae_configs.h"
 #include "../../kalman_vae_b200/csrc/kvae_fwd.cuh"
+#include "../../kalman_vae_b200/csrc/kvae_elbo.cuh"
+#include "../../kalman_vae_b200/csrc/kvae_bwd.cuh"
 
 using namespace kvae;
 
@@ -39,6 +41,88 @@ extern "C" int hostsim_fwd(int N, int P, int M, int K, int switching, int force_
                      else run_fwd<Cfg<n, p, m, k, 1, true, true, false>>(a, hp, smooth); }              \
     else { if (force_mem) run_fwd<Cfg<n, p, m, k, 1, false, false, true>>(a, hp, smooth);               \
            else run_fwd<Cfg<n, p, m, k, 1, false, false, false>>(a, hp, smooth); }                      \
+    return 0;                                                                                           \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return -1;
+}
+
+template <class C> static void run_elbo(const Args& a, const HostParams& hp, float jitter, double* acc5) {
+  std::vector<float> base(Base<C>::total);
+  for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
+  std::vector<float> tiles(Tiles<C>::total + 4);
+  Group<C::L, C::R> g{0};
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int b = 0; b < a.B; ++b) elbo_sweep<C>(a, base.data(), tiles.data(), g, b, true, jitter, acc);
+  for (int i = 0; i < 5; ++i) acc5[i] = acc[i];
+}
+
+extern "C" int hostsim_elbo(int N, int P, int M, int K, int switching, int force_mem, int B, int T,
+                            const float* Y, const float* U, const float* mask, const float* alpha, const float* eps,
+                            const float* A, const float* Bm, const float* C, const float* Q, const float* R,
+                            const float* mu0, const float* S0, float* mu_s, float* Sig_s, float jitter,
+                            double* acc5, int* info) {
+  Args a{};
+  a.B = B; a.T = T; a.Y = Y; a.U = U; a.mask = mask; a.alpha = alpha; a.eps = eps;
+  a.mu_s = mu_s; a.Sig_s = Sig_s; a.info = info;
+  HostParams hp{A, Bm, C, Q, R, mu0, S0};
+#define X(n, p, m, k)                                                                                   \
+  if (N == n && P == p && M == m && K == k) {                                                           \
+    if (switching) { if (force_mem) run_elbo<Cfg<n, p, m, k, 1, true, true, true>>(a, hp, jitter, acc5);   \
+                     else run_elbo<Cfg<n, p, m, k, 1, true, true, false>>(a, hp, jitter, acc5); }          \
+    else { if (force_mem) run_elbo<Cfg<n, p, m, k, 1, false, false, true>>(a, hp, jitter, acc5);           \
+           else run_elbo<Cfg<n, p, m, k, 1, false, false, false>>(a, hp, jitter, acc5); }                  \
+    return 0;                                                                                           \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return -1;
+}
+
+template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParams& hp, double* gp, float** dbg) {
+  std::vector<float> base(Base<C>::total);
+  for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
+  std::vector<float> tiles(BTiles<C>::total + 4);
+  const size_t nn = (size_t)a.B * a.T * C::N * C::N, nv = (size_t)a.B * a.T * C::N;
+  std::vector<float> wSf(nn), wSp(nn), wmf(nv), wmp(nv);
+  w.w_Sig_f = wSf.data(); w.w_Sig_p = wSp.data(); w.w_mu_f = wmf.data(); w.w_mu_p = wmp.data();
+  Group<C::L, C::R> g{0};
+  for (int i = 0; i < GradAcc<C>::PSZ; ++i) gp[i] = 0.0;
+  for (int b = 0; b < a.B; ++b) {
+    GradAcc<C> acc;
+    acc.zero();
+    bwd_sweep3<C>(a, w, base.data(), tiles.data(), g, b, true, acc);
+    bwd_sweep4<C>(a, w, base.data(), tiles.data(), g, b, true, acc);
+    acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
+  }
+  if (dbg) {
+    memcpy(dbg[0], wSf.data(), nn * 4); memcpy(dbg[1], wSp.data(), nn * 4);
+    memcpy(dbg[2], wmf.data(), nv * 4); memcpy(dbg[3], wmp.data(), nv * 4);
+  }
+}
+
+extern "C" int hostsim_bwd(int N, int P, int M, int K, int switching, int force_mem, int B, int T,
+                           const float* Y, const float* U, const float* mask, const float* alpha, const float* eps,
+                           const float* A, const float* Bm, const float* C, const float* Q, const float* R,
+                           const float* mu0, const float* S0,
+                           float* mu_f, float* Sig_f, float* mu_p, float* Sig_p, float* mu_s, float* Sig_s,
+                           float c_elbo, float jitter, const float** cot9,
+                           float* dY, float* dU, float* dalpha, double* gparams, int* info, float** dbg) {
+  Args a{};
+  a.B = B; a.T = T; a.Y = Y; a.U = U; a.mask = mask; a.alpha = alpha; a.eps = eps;
+  a.mu_f = mu_f; a.Sig_f = Sig_f; a.mu_p = mu_p; a.Sig_p = Sig_p; a.mu_s = mu_s; a.Sig_s = Sig_s; a.info = info;
+  BwdArgs w{};
+  w.c_mu_s = cot9[0]; w.c_Sig_s = cot9[1]; w.c_mu_f = cot9[2]; w.c_Sig_f = cot9[3]; w.c_mu_p = cot9[4]; w.c_Sig_p = cot9[5];
+  w.c_A = cot9[6]; w.c_B = cot9[7]; w.c_C = cot9[8];
+  w.dY = dY; w.dU = dU; w.dalpha = dalpha; w.c_elbo = c_elbo; w.jitter = jitter;
+  HostParams hp{A, Bm, C, Q, R, mu0, S0};
+#define X(n, p, m, k)                                                                                   \
+  if (N == n && P == p && M == m && K == k) {                                                           \
+    if (switching) { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, true, true, true>>(a, w, hp, gparams, dbg);      \
+                     else run_bwd<Cfg<n, p, m, k, 1, true, true, false>>(a, w, hp, gparams, dbg); }             \
+    else { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, false, false, true>>(a, w, hp, gparams, dbg);              \
+           else run_bwd<Cfg<n, p, m, k, 1, false, false, false>>(a, w, hp, gparams, dbg); }                     \
     return 0;                                                                                           \
   }
   KVAE_FOR_EACH_SHAPE(X)
