@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — Kalman filter + RTS smoother + ELBO forward and explicit-adjoint backward on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1], "cfg2"): B=8192 sequences PER GPU (weak scaling), T=20, z_dim=4,
+a_dim=2, u_dim=4, K=3 mixture modes, synthetic bouncing-ball-shaped observations, alpha=softmax(N(0,1)),
+mask=1.  One step = smooth (filter+smoother) + elbo + backward (all gradients).
+
+One JSON line on stdout (rank 0):
+  value      sequence-steps/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API (KalmanFilter.smooth/.elbo/.backward) with pinned HOST
+             buffers: H2D of the step's inputs and D2H of loss + parameter gradients inside the timed region
+  roofline   dominant kernel's algorithmic HBM bytes / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU port of the reference algorithm (oracle/) timed on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from kalman_vae_b200.synthetic import CONFIGS, Shape, make_case  # noqa: E402
+
+METRIC = "kalman_filter_smoother_fwd_bwd_sequence_steps_per_sec"
+UNIT = "sequence-steps/s"
+WORKLOAD = "cfg2"
+
+
+def algorithmic_bytes(shape: Shape):
+    """bytes per sequence-step with every tensor of the public contract touched once."""
+    n, p, m, K = shape.n, shape.p, shape.m, shape.K
+    c = 0 if shape.c_shared else 1
+    fwd = 4 * (p + m + 1 + K + 3 * n + 4 * n * n + n * m + c * p * n)
+    elbo = 4 * n
+    bwd = 4 * (2 * p + m + 1 + 2 * K + n + 3 * n + 3 * n * n)
+    return dict(fwd=fwd, elbo=elbo, bwd=bwd, total=fwd + elbo + bwd)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU port of the reference algorithm (oracle/), all host threads
+# ----------------------------------------------------------------------------------------------------
+def cpu_steps_per_sec(shape: Shape, sample_B: int, reps: int, warmup: int = 1):
+    from oracle import kalman_oracle as ko   # the one place bench.py may execute oracle/
+    case = make_case(Shape(sample_B, shape.T, shape.n, shape.p, shape.m, shape.K, shape.q_per_mode, shape.c_shared), seed=10)
+    for _ in range(warmup):
+        ko.smooth_elbo_fwd_bwd(case, torch.float32, backward=True)
+    best = float("inf")
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ko.smooth_elbo_fwd_bwd(case, torch.float32, backward=True)
+        dt = time.perf_counter() - t0
+        times.append(dt)
+        best = min(best, dt)
+    return sample_B * shape.T / best, times
+
+
+def run_reference(args, rank, world):
+    """Times the reference algorithm (CPU port, all host threads).  Each step is a bounded sample of the
+    cfg2 batch, sized from a short calibration so that warmup+steps finish in about two minutes."""
+    if rank != 0:
+        return
+    from oracle import kalman_oracle as ko
+    shape = CONFIGS[WORKLOAD]
+    threads = torch.get_num_threads()
+    t0 = time.perf_counter()
+    calib = make_case(Shape(512, shape.T, shape.n, shape.p, shape.m, shape.K), seed=10)
+    ko.smooth_elbo_fwd_bwd(calib, torch.float32, backward=True)
+    t1 = time.perf_counter()
+    ko.smooth_elbo_fwd_bwd(calib, torch.float32, backward=True)
+    per_seq = (time.perf_counter() - t1) / 512
+    budget = 120.0
+    sample_B = int(min(shape.B, max(256, budget / ((args.steps + args.warmup) * per_seq))))
+    sample_B = max(256, (sample_B // 256) * 256)
+    case = make_case(Shape(sample_B, shape.T, shape.n, shape.p, shape.m, shape.K), seed=10)
+    for _ in range(args.warmup):
+        ko.smooth_elbo_fwd_bwd(case, torch.float32, backward=True)
+    tt = []
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        ko.smooth_elbo_fwd_bwd(case, torch.float32, backward=True)
+        tt.append(time.perf_counter() - t1)
+    ms = 1e3 * sum(tt) / len(tt)
+    value = sample_B * shape.T / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: B={shape.B} sequences per GPU, T={shape.T}, n={shape.n}, p={shape.p}, m={shape.m}, "
+                               f"K={shape.K}; smooth+elbo forward and backward",
+                   "reference_arm": "reference algorithm on the host CPU (oracle/ port: torch CPU ops in the reference's op "
+                                    "order + autograd), per-step sample of the cfg2 batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample_B} of {shape.B} sequences x T={shape.T} per step, mean of {args.steps} steps; "
+                                   f"os.cpu_count()={os.cpu_count()}, torch threads={threads}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------------
+def run_cuda(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from kalman_vae_b200 import KalmanFilter, capi
+    from kalman_vae_b200.dyn_param import PrecomputedWeights
+    from kalman_vae_b200.engine import KalmanStep
+    from kalman_vae_b200.functional import Problem
+
+    capi.lib()   # fail loudly if the CUDA library is missing
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shape = CONFIGS[WORKLOAD]
+    ab = algorithmic_bytes(shape)
+    peak, peak_src = peaks()
+    lanes = args.lanes
+
+    # ---- device-resident buffer sets, rotated so that consecutive steps never re-use L2-resident data
+    nsets = args.buffer_sets
+    sets = []
+    for s in range(nsets):
+        case = make_case(shape, seed=10 + 97 * rank + s)
+        g = {k: (v.to(dev).contiguous() if torch.is_tensor(v) else v) for k, v in case.items()}
+        pb = Problem(g["Y"], g["U"], g["mask"], g["alpha"], g["A"], g["B"], g["C"], g["Q"], g["R"], g["mu0"], g["Sigma0"],
+                     shape.q_per_mode, shape.c_shared, lanes=lanes)
+        sets.append(KalmanStep(pb, g["eps"], use_graphs=not args.no_graphs, need_dU=False))
+    lanes_used = capi.pick_lanes(sets[0].pb.dims) if lanes == 0 else lanes
+    set_bytes = sum(t.numel() * t.element_size() for t in
+                    [sets[0].pb.Y, sets[0].pb.U, sets[0].pb.alpha, sets[0].eps, sets[0].st.mus_filt, sets[0].st.Sigmas_filt,
+                     sets[0].st.mus_pred, sets[0].st.Sigmas_pred, sets[0].st.mus_smooth, sets[0].st.Sigmas_smooth,
+                     sets[0].A_list, sets[0].B_list, sets[0].C_list, sets[0].ws_bwd])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    stream = torch.cuda.current_stream(dev)
+    for i in range(max(args.warmup, 3)):
+        sets[i % nsets].step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        sets[i % nsets].step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = world * shape.B * shape.T / (ms_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events around each C-ABI call, rotating sets), for the roofline
+    def time_call(fn_name, reps=20):
+        evs = []
+        for i in range(3):
+            getattr(sets[i % nsets], fn_name)()
+        torch.cuda.synchronize(dev)
+        for i in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            getattr(sets[i % nsets], fn_name)()
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        return statistics.median(x.elapsed_time(y) for x, y in evs) * 1e-3
+
+    kt = {}
+    if rank == 0:
+        from kalman_vae_b200 import capi as _c
+        for s in sets:   # un-graphed single calls for kernel timing
+            s._only_fwd = lambda s=s: _c.filter_smooth_fwd(s.pb.dims, s._inputs, s._states, s.A_list, s.B_list, s.C_list, s.info, s.dev)
+            s._only_elbo = lambda s=s: _c.elbo_fwd(s.pb.dims, s._inputs, s._states, s.eps, s.jitter, s.terms, s.ws_elbo, s.info, s.dev)
+        kt["k_filter_smooth"] = time_call("_only_fwd")
+        kt["k_elbo(+final)"] = time_call("_only_elbo")
+        kt["k_bwd(+param_final)"] = time_call("_bwd")
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        case = make_case(shape, seed=1234 + rank)
+        dyn = PrecomputedWeights(case["A"], case["B"], case["C"], case["Q"] if shape.q_per_mode else None,
+                                 switching=shape.q_per_mode)
+        kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, case["mu0"], case["Sigma0"], dyn, lanes=lanes).to(dev)
+        kf.strict = False
+        kf.check_info = False
+        host = {k: case[k].pin_memory() for k in ("Y", "U", "mask", "alpha", "eps")}
+        h2d = sum(v.numel() * 4 for v in host.values())
+        out_host = torch.empty(1 + sum(p.numel() for p in dyn.parameters()), pin_memory=True)
+        d2h = out_host.numel() * 4
+        params = list(dyn.parameters())
+
+        def e2e_step():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            Y = d["Y"].requires_grad_(True)
+            dyn.set_weights(d["alpha"].requires_grad_(True))
+            kf._draw_eps = lambda B, T, n, like: d["eps"]
+            outs = kf.smooth(Y, d["U"], d["mask"])
+            val = kf.elbo(outs[0], outs[1], Y, d["U"], outs[6], outs[7], outs[8], mask=d["mask"])
+            grads = torch.autograd.grad(val, [Y, dyn.alpha] + params)
+            if world > 1:
+                from kalman_vae_b200.dist import allreduce_param_grads
+                allreduce_param_grads(list(grads[2:]))
+            flat = torch.cat([val.reshape(1)] + [g.reshape(-1) for g in grads[2:]])
+            out_host.copy_(flat, non_blocking=True)
+
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        b.record(stream)
+        barrier()
+        t2 = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t2) / args.steps
+        e2e = {"value": world * shape.B * shape.T / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+               "api": "KalmanFilter.smooth -> .elbo -> autograd.grad (pinned host inputs, loss+param grads read back)"}
+
+    if rank == 0:
+        # dominant kernel
+        dom = max(kt, key=kt.get)
+        dom_bytes = {"k_filter_smooth": ab["fwd"], "k_elbo(+final)": ab["elbo"] + 4 * (shape.n + shape.n ** 2),
+                     "k_bwd(+param_final)": ab["bwd"]}[dom] * shape.B * shape.T
+        achieved = dom_bytes / kt[dom] / 1e9
+        cpu_val, cpu_times = (None, [])
+        cpu = None
+        if not args.no_cpu:
+            reps = 3
+            cpu_val, cpu_times = cpu_steps_per_sec(shape, shape.B, reps)
+            cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"full {WORKLOAD} batch ({shape.B} sequences x T={shape.T}) smooth+elbo fwd+bwd with the oracle "
+                             f"(torch CPU ops in the reference's op order), best of {reps}; os.cpu_count()={os.cpu_count()}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: B={shape.B} sequences per GPU, T={shape.T}, n={shape.n}, p={shape.p}, m={shape.m}, "
+                                   f"K={shape.K}; smooth+elbo forward and explicit-adjoint backward",
+                       "lanes_per_sequence": lanes_used, "cuda_graphs": not args.no_graphs,
+                       "l2": f"{nsets} rotating buffer sets of {set_bytes / 2**20:.0f} MiB each (> 126 MB L2 in total)",
+                       "sharding": "batch dimension, contiguous per rank; all-reduce of 5 ELBO sums + flat parameter gradients"},
+            "e2e": e2e, "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_seq_step": ab, "kernel_seconds": kt,
+                         "whole_step_frac": ab["total"] * world * shape.B * shape.T / (ms_step * 1e-3) / 1e9 / (peak * world)},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--buffer-sets", type=int, default=6)
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,42 @@ class DynamicsParameter(nn.Module):
         return alpha
 
 
+class PrecomputedWeights(nn.Module):
+    """dyn_params protocol object whose mixture weights alpha [B,T,K] are supplied by the caller
+    (e.g. computed elsewhere or streamed from the host); base matrices are ordinary parameters.
+    switching=True selects the SKVAE conventions (Q per mode, shared C)."""
+
+    def __init__(self, A, B, C, Q=None, switching=False):
+        super().__init__()
+        self.is_switching_dynamics = bool(switching)
+        self.K = A.size(0)
+        self.n, self.m, self.p = A.size(1), B.size(2), C.size(1)
+        self.A = nn.Parameter(A.clone())
+        self.B = nn.Parameter(B.clone())
+        self.C = nn.Parameter(C.clone())
+        if switching:
+            self.Q = nn.Parameter(Q.clone())
+        self.alpha = None
+        self.state_seq = None
+        self.lstm_state = None
+
+    def set_weights(self, alpha):
+        self.alpha = alpha
+
+    def reset_state(self):
+        self.state_seq = None
+
+    def compute_weights(self, a_seq, is_training=True):
+        B, T, _ = a_seq.shape
+        self.state_seq = self.alpha
+        self.log_qseq = torch.zeros(B, T, device=a_seq.device, dtype=a_seq.dtype)
+        self.log_pseq = torch.zeros(B, T, device=a_seq.device, dtype=a_seq.dtype)
+        return self.alpha
+
+    def elbo_terms(self):
+        return self.log_qseq, self.log_pseq
+
+
 class StickyRegimePrior:
     """Mirror of switch_dyn_param.py:98-110."""
 

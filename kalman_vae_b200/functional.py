@@ -163,7 +163,6 @@ class SmoothFunction(torch.autograd.Function):
             outs.append(C_list)
         if smooth:
             outs = [st.mus_smooth, st.Sigmas_smooth] + outs
-        ctx.mark_non_differentiable()
         return tuple(outs)
 
     @staticmethod

@@ -54,6 +54,7 @@ class KalmanFilter(nn.Module):
         self.register_buffer("Sigma0", Sigma0.clone())
         self.lanes = lanes              # 0: library picks lanes per sequence
         self.check_info = check_info    # read the device 'non-positive pivot' flag after elbo()
+        self.strict = True              # verify that elbo() sees the same y/mask values as smooth()
         self._mask_cache = None
 
     # ------------------------------------------------------------------ helpers
@@ -117,7 +118,11 @@ class KalmanFilter(nn.Module):
         B, T, _ = Y.shape
         mask_t = self._mask(mask, B, T, Y)
         dyn = self.dyn_params
-        if (not dyn.is_switching_dynamics) and dyn.K > 1 and not self._mask_is_ones(mask_t):
+        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and not self._mask_is_ones(mask_t):
+            if torch.is_grad_enabled() and (Y.requires_grad or any(p.requires_grad for p in dyn.parameters())):
+                raise NotImplementedError(
+                    "lstm dynamics with missing observations is forward-only here (imputation, as in "
+                    "KVAE.impute); wrap the call in torch.no_grad()")
             return self._run_stepwise_lstm(Y, U, mask_t, smooth)
         alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
         pb = self._problem(Y, U, mask_t, alpha, A, Bm, C, Q, qpm, csh)
@@ -230,13 +235,13 @@ class KalmanFilter(nn.Module):
         if Q_list is not None:
             raise NotImplementedError("elbo(): explicit Q_list is not supported; Q is mixed from alpha in the kernel")
         mask_t = self._mask(mask, B, T, y_t)
-        if (mask_t is None) != (pb.mask is None) or (mask_t is not None and mask_t.data_ptr() != pb.mask.data_ptr()
-                                                       and not torch.equal(mask_t.float(), pb.mask)):
-            raise NotImplementedError("elbo(): mask differs from the one given to smooth()")
-        if y_t.data_ptr() != pb.Y.data_ptr() and not torch.equal(y_t.detach().float(), pb.Y):
-            raise NotImplementedError("elbo(): y_t differs from the observations given to smooth()")
-        eps = torch.empty(B, T, n, dtype=y_t.dtype, device=y_t.device).normal_()   # == MultivariateNormal.rsample draw
-        eps = prep(eps)
+        if self.strict:   # value checks cost a host sync each; switch off with kf.strict = False
+            if (mask_t is None) != (pb.mask is None) or (mask_t is not None and mask_t.data_ptr() != pb.mask.data_ptr()
+                                                           and not torch.equal(mask_t.float(), pb.mask)):
+                raise NotImplementedError("elbo(): mask differs from the one given to smooth()")
+            if y_t.data_ptr() != pb.Y.data_ptr() and not torch.equal(y_t.detach().float(), pb.Y):
+                raise NotImplementedError("elbo(): y_t differs from the observations given to smooth()")
+        eps = prep(self._draw_eps(B, T, n, y_t))
         dyn = self.dyn_params
         extra = None
         if dyn.is_switching_dynamics:
@@ -257,6 +262,10 @@ class KalmanFilter(nn.Module):
                 "kvae elbo: a Cholesky factorisation met a non-positive pivot (the reference's "
                 "_safe_cholesky would retry with 10x jitter, kalman_filter.py:291-296)")
         return val
+
+    def _draw_eps(self, B, T, n, like):
+        """The standard-normal draw behind MultivariateNormal.rsample (kalman_filter.py:351)."""
+        return torch.empty(B, T, n, dtype=like.dtype, device=like.device).normal_()
 
     def filter_step(self, mu_t_t, Sigma_t_t, y_t, u_t, A, B, C, Q, mask_t=None):
         raise NotImplementedError("per-step form with explicit matrices: use filter() (single-step launches are "

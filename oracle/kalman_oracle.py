@@ -171,7 +171,7 @@ OUT_NAMES = ["mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred
              "A_list", "B_list", "C_list"]
 
 
-def run_case(case: dict, dtype=torch.float32, want_grads=True, cotangents=None):
+def run_case(case: dict, dtype=torch.float32, want_grads=True, cotangents=None, with_elbo=True):
     g = lambda k: case[k].to(dtype).clone()
     Y, U, mask, alpha, eps = g("Y"), g("U"), g("mask"), g("alpha"), g("eps")
     A, Bm, C, Q, R, mu0, Sigma0 = g("A"), g("B"), g("C"), g("Q"), g("R"), g("mu0"), g("Sigma0")
@@ -182,8 +182,10 @@ def run_case(case: dict, dtype=torch.float32, want_grads=True, cotangents=None):
             t.requires_grad_(True)
     outs, Q_seq = smooth(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, c_shared, q_per_mode)
     res = {n: o.detach().clone() for n, o in zip(OUT_NAMES, outs)}
-    val = elbo(outs[0], outs[1], Y, U, outs[6], outs[7], outs[8], Q_seq, R, mu0, Sigma0, mask, eps)
-    res["elbo"] = val.detach().clone()
+    val = 0.0
+    if with_elbo:
+        val = elbo(outs[0], outs[1], Y, U, outs[6], outs[7], outs[8], Q_seq, R, mu0, Sigma0, mask, eps)
+        res["elbo"] = val.detach().clone()
     if want_grads:
         loss = val
         if cotangents is not None:

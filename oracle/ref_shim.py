@@ -149,7 +149,7 @@ class fixed_eps:
         return False
 
 
-def run_reference_case(case: dict, dtype=torch.float32, want_grads=True, cotangents=None):
+def run_reference_case(case: dict, dtype=torch.float32, want_grads=True, cotangents=None, with_elbo=True):
     """Runs the unmodified reference KalmanFilter.smooth + .elbo (+ backward) on a case dict
     (see oracle/cases.py) and returns a dict of numpy-convertible tensors."""
     ref = load()
@@ -172,11 +172,12 @@ def run_reference_case(case: dict, dtype=torch.float32, want_grads=True, cotange
     names = ["mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
              "A_list", "B_list", "C_list"]
     res = {n: o.detach().clone() for n, o in zip(names, outs)}
-    with fixed_eps(eps):
-        elbo = kf.elbo(outs[0], outs[1], Yv, Uv, outs[6], outs[7], outs[8], mask=mask)
-    res["elbo"] = elbo.detach().clone()
+    if with_elbo:
+        with fixed_eps(eps):
+            elbo = kf.elbo(outs[0], outs[1], Yv, Uv, outs[6], outs[7], outs[8], mask=mask)
+        res["elbo"] = elbo.detach().clone()
     if want_grads:
-        loss = elbo
+        loss = elbo if with_elbo else 0.0
         if cotangents is not None:
             for n, o in zip(names, outs):
                 if cotangents.get(n) is not None:

@@ -1,0 +1,55 @@
+"""CPU test: the C-ABI shared library loads and exports every symbol include/kvae_kalman.h declares
+(no compute calls without a GPU), and the host-side argument checks reject bad shapes."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from kalman_vae_b200 import build as kbuild
+from kalman_vae_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    kbuild.build()
+    return ctypes.CDLL(capi.LIB_PATH)
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "kvae_kalman.h")).read()
+    declared = set(re.findall(r"\b(kvae_[a-z_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+def test_abi_version_and_support_table(lib):
+    L = capi.lib()
+    assert L.kvae_abi_version() == 1
+    ok = capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 0)
+    assert capi.supported(ok)
+    assert capi.pick_lanes(ok) == 4                      # small batch -> widest lane group
+    assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 1
+    assert capi.supported(capi.make_dims(8, 20, 16, 8, 16, 8, True, True, 16))
+    assert not capi.supported(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0))     # shape not instantiated
+    assert not capi.supported(capi.make_dims(8, 20, 4, 2, 4, 3, True, False, 0))      # mixed variant
+    assert not capi.supported(capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 3))     # lanes must divide n
+
+
+def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
+    L = capi.lib()
+    rc = L.kvae_kf_filter_smooth_fwd(None, None, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"null" in L.kvae_last_error()
+
+
+def test_cpu_tensors_raise():
+    import torch
+    from kalman_vae_b200.functional import Problem
+    from kalman_vae_b200.synthetic import Shape, make_case
+    c = make_case(Shape(2, 3, 4, 2, 4, 3))
+    pb = Problem(c["Y"], c["U"], c["mask"], c["alpha"], c["A"], c["B"], c["C"], c["Q"], c["R"], c["mu0"], c["Sigma0"], False, False)
+    with pytest.raises(capi.KvaeError):
+        pb.inputs()        # CPU tensors: no CPU implementation exists

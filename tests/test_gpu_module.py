@@ -1,0 +1,164 @@
+"""GPU tests of the drop-in boundary: kalman_vae_b200.KalmanFilter used exactly like the reference's
+kvae.kalman.kalman_filter.KalmanFilter (same constructor / calls / tuples / layouts), checked against
+golden vectors of the unmodified reference (kalman_*: fixed mixture weights incl. autograd gradients;
+kvae_*: the whole reference KVAE with its real LSTM / bi-GRU dynamics networks on the recipe of the
+reference's own tests/test_imputation_stability.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from kalman_vae_b200 import KalmanFilter, DynamicsParameter, SwitchingDynamicsParameter
+from kalman_vae_b200 import dyn_param as dp_mod
+from kalman_vae_b200.dyn_param import MarkovVariationalRegimePosterior, StickyRegimePrior
+from tests._util import GOLDEN, GRAD_NAMES, OUT_NAMES, check_close, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class FixedWeights(nn.Module):
+    """dyn_params protocol object with externally given mixture weights (test double of the LSTM / GRU)."""
+
+    def __init__(self, case):
+        super().__init__()
+        self.is_switching_dynamics = bool(case["q_per_mode"])
+        self.A, self.B, self.C = (nn.Parameter(case[k].clone()) for k in ("A", "B", "C"))
+        if self.is_switching_dynamics:
+            self.Q = nn.Parameter(case["Q"].clone())
+        self.alpha = nn.Parameter(case["alpha"].clone())
+        self.K = self.A.shape[0]
+        self.state_seq = None
+
+    def reset_state(self):
+        self.state_seq = None
+
+    def compute_weights(self, a_seq, is_training=True):
+        B, T, _ = self.alpha.shape
+        self.state_seq = self.alpha
+        self.log_qseq = torch.zeros(B, T, device=self.alpha.device)
+        self.log_pseq = torch.zeros(B, T, device=self.alpha.device)
+        return self.alpha
+
+    def elbo_terms(self):
+        return self.log_qseq, self.log_pseq
+
+
+def make_kf(case):
+    dyn = FixedWeights(case)
+    kf = KalmanFilter(1.0, 1.0, case["mu0"], case["Sigma0"], dyn)
+    kf.R.copy_(case["R"])
+    if not case["q_per_mode"]:
+        kf.Q.copy_(case["Q"])
+    return kf.to(DEV), dyn
+
+
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_lstm_default", "kalman_switch", "kalman_fractional", "kalman_n16",
+                                  "kalman_rocket"])
+def test_smooth_elbo_backward_through_module_api(name, monkeypatch):
+    case, cot, r32, r64 = load_golden(name)
+    kf, dyn = make_kf(case)
+    assert (kf.n, kf.m, kf.p) == (case["A"].shape[-1], case["B"].shape[-1], case["C"].shape[-2])
+    Y = case["Y"].to(DEV).requires_grad_(True)
+    U = case["U"].to(DEV).requires_grad_(True)
+    mask = case["mask"].to(DEV)
+    dyn.reset_state()
+    outs = kf.smooth(Y, U, mask)
+    assert len(outs) == 9
+    B, T, p = case["Y"].shape
+    n = kf.n
+    assert outs[0].shape == (B, T, n, 1) and outs[1].shape == (B, T, n, n) and outs[8].shape == (B, T, p, n)
+    for k, o in zip(OUT_NAMES, outs):
+        check_close(f"{name}.{k}", o, r32[k], r64[k])
+    # elbo(): the eps draw is torch.empty(B,T,n).normal_() on the device; inject the golden's draw
+    eps = case["eps"].to(DEV)
+    monkeypatch.setattr(kf, "_draw_eps", lambda B, T, n, like: eps)
+    val = kf.elbo(outs[0], outs[1], Y, U, outs[6], outs[7], outs[8], mask=mask)
+    check_close(f"{name}.elbo", val, r32["elbo"], r64["elbo"])
+    loss = val
+    if cot:
+        for k, o in zip(OUT_NAMES, outs):
+            if k in cot:
+                loss = loss + (cot[k].to(DEV) * o).sum()
+    params = [Y, U, dyn.alpha, dyn.A, dyn.B, dyn.C] + ([dyn.Q] if case["q_per_mode"] else [])
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    for k, g in zip(GRAD_NAMES, grads):
+        assert g is not None, k
+        check_close(f"{name}.{k}", g, r32[k], r64[k])
+
+
+def test_filter_returns_seven_tuple_and_matches():
+    case, _, r32, r64 = load_golden("kalman_lstm")
+    kf, dyn = make_kf(case)
+    with torch.no_grad():
+        outs = kf.filter(case["Y"].to(DEV), case["U"].to(DEV), case["mask"].to(DEV))
+    assert len(outs) == 7
+    for k, o in zip(OUT_NAMES[2:], outs):
+        check_close(k, o, r32[k], r64[k])
+
+
+def test_cpu_input_raises():
+    case = load_golden("kalman_lstm")[0]
+    kf, _ = make_kf(case)
+    with pytest.raises(Exception):
+        kf.smooth(case["Y"], case["U"], case["mask"])
+
+
+def _load_kvae(kind):
+    z = np.load(os.path.join(GOLDEN, f"kvae_{kind}.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _kvae_kalman_block(kind, g):
+    """The Kalman block of the reference KVAE (model.py:33-78) built from this package's classes."""
+    K, n, p, m, hidden = 3, 4, 2, 4, 50
+    A, Bm, C = torch.zeros(K, n, n), torch.zeros(K, n, m), torch.zeros(K, p, n)
+    if kind == "switching":
+        dyn = SwitchingDynamicsParameter(A, Bm, C, Q=torch.zeros(K, n, n), prior=StickyRegimePrior(K, p_stay=0.8),
+                                         hidden_lstm=hidden,
+                                         markov_regime_posterior=MarkovVariationalRegimePosterior(K, input_dim=p, hidden_size=hidden))
+        dyn.tau = 1.0                                                      # config.tau_init (model.py:62)
+    else:
+        dyn = DynamicsParameter(A, Bm, C, hidden_lstm=hidden)
+    kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, torch.zeros(n), 20.0 * torch.eye(n), dyn)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    missing, unexpected = kf.load_state_dict(sd, strict=True)              # same keys as the reference's state dict
+    assert not missing and not unexpected
+    return kf.to(DEV).eval(), dyn
+
+
+@pytest.mark.parametrize("kind", ["lstm", "switching"])
+def test_kvae_imputation_recipe_matches_reference(kind, monkeypatch):
+    """tests/test_imputation_stability.py recipe, from the encoder sample `a` onwards: masked frames 4:10.
+    lstm: alpha_t depends on the running prediction -> the stepwise (per-step launch) path is exercised."""
+    g = _load_kvae(kind)
+    kf, dyn = _kvae_kalman_block(kind, g)
+    a, u, mask = g["a"].to(DEV), g["u"].to(DEV), g["mask"].to(DEV)
+    if kind == "switching":
+        noise = g["gumbel_noise"].to(DEV)
+        calls = {"i": 0}
+
+        def det_gumbel_softmax(logits, tau=1.0, hard=False, dim=-1):
+            gn = noise[calls["i"] % noise.shape[0]]
+            calls["i"] += 1
+            y_soft = ((logits + gn) / tau).softmax(dim)
+            if hard:
+                idx = y_soft.max(dim, keepdim=True)[1]
+                return torch.zeros_like(logits).scatter_(dim, idx, 1.0)
+            return y_soft
+        monkeypatch.setattr(dp_mod, "gumbel_softmax", det_gumbel_softmax)
+    with torch.no_grad():
+        dyn.reset_state()
+        outs = kf.smooth(a.clone(), u.clone(), mask)
+    names = OUT_NAMES
+    for k, o in zip(names, outs):
+        ref = g[k]
+        err = float((o.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
+        assert err < 2e-5, (k, err)
+    assert torch.allclose(dyn.state_seq.cpu(), g["state_probs"], atol=2e-6)
+    a_imputed = (outs[8] @ outs[0]).squeeze(-1)                             # model.py:280-281
+    a_filtered = (outs[8] @ outs[2]).squeeze(-1)                            # model.py:287-288
+    assert torch.allclose(a_imputed.cpu(), g["a_imputed"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(a_filtered.cpu(), g["a_filtered"], rtol=1e-4, atol=1e-6)
