@@ -21,6 +21,9 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 
 
 def shapes():
+    env = os.environ.get("KVAE_SHAPES")   # development: "4,2,4,3;16,8,16,8" builds only those shapes
+    if env:
+        return [tuple(int(x) for x in part.split(",")) for part in env.split(";") if part]
     txt = open(os.path.join(CSRC, "kvae_configs.h")).read()
     body = txt[txt.index("#define KVAE_FOR_EACH_SHAPE"):]
     return [tuple(int(x) for x in m) for m in re.findall(r"X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", body)]
@@ -58,7 +61,13 @@ def build(force=False, verbose=False):
                "-c", os.path.join(CSRC, "kvae_shape.cu"), "-o", o]
         jobs.append((cmd, o))
     o = os.path.join(OBJ, "capi.o")
-    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_capi.cu"), "-o", o], o))
+    extra = []
+    if os.environ.get("KVAE_SHAPES"):
+        hdr = os.path.join(OBJ, "shape_list_override.h")
+        with open(hdr, "w") as f:
+            f.write("#define KVAE_FOR_EACH_SHAPE(X) " + " ".join(f"X({n},{p},{m},{k})" for (n, p, m, k) in shapes()) + "\n")
+        extra = ["--pre-include", hdr]
+    jobs.append(([NVCC, *ARCH, *FLAGS, *extra, "-c", os.path.join(CSRC, "kvae_capi.cu"), "-o", o], o))
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
     if verbose:

@@ -23,18 +23,8 @@ struct BwdArgs {
   float jitter;
 };
 
-// Tiles for the backward sweeps (six general + persistent + two [N x P] + vectors)
-template <class C> struct BTiles {
-  static constexpr int szNN = Tiles<C>::szNN, szNP = Tiles<C>::szNP;
-  static constexpr int nNN = 8;
-  static KV_FN constexpr int oT(int i) { return i * szNN; }
-  static constexpr int oC = nNN * szNN;
-  static constexpr int oK = oC + szNP;
-  static constexpr int oP = oK + szNP;
-  static constexpr int oV = oP + szNP;
-  static constexpr int oV2 = oV + pad4(C::N);
-  static constexpr int total = C::MEM ? (oV2 + pad4(C::N)) : 0;
-};
+// Per-warp tiles of the backward sweeps: 8 [n x n] + 3 [n x p] + 2 vector slots.
+template <class C> using BTiles = TileSet<C::L, C::R, C::P, 8, 3, 2, C::MEM>;
 
 // own entries of a replicated vector
 template <class C> KV_FN void pick_own(const Group<C::L, C::R>& g, const float (&full)[C::N], float (&own)[C::R]) {
@@ -135,15 +125,12 @@ template <class C> struct GradAcc {
 // sweep 3: ELBO adjoint (A.3) + smoother adjoint (A.4), forward in time
 // ---------------------------------------------------------------------------------------
 template <class C>
-KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, float* tiles, const Group<C::L, C::R>& g,
+KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const BTiles<C>& tl, const Group<C::L, C::R>& g,
                       int b, bool active, GradAcc<C>& acc) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L, K = C::K;
   constexpr bool MEM = C::MEM;
-  using BT = BTiles<C>;
-  float* T0 = tiles + BT::oT(0); float* T1 = tiles + BT::oT(1); float* T2 = tiles + BT::oT(2);
-  float* T3 = tiles + BT::oT(3); float* T4 = tiles + BT::oT(4); float* T5 = tiles + BT::oT(5);
-  float* T6 = tiles + BT::oT(6); float* TP = tiles + BT::oT(7);
-  float* VB = tiles + BT::oV; float* VB2 = tiles + BT::oV2;
+  const TileRef T0 = tl.nn(0), T1 = tl.nn(1), T2 = tl.nn(2), T3 = tl.nn(3), T4 = tl.nn(4), T5 = tl.nn(5), TP = tl.nn(7);
+  const TileRef VB = tl.vec(0), VB2 = tl.vec(1);
   // elbo_sample / sym_jitter_rows use Tiles<C> offsets oX0 (= T0) and oV (remapped below)
   const int row0 = g.row0();
   const int T = a.T;
@@ -158,7 +145,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, float*
     KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) ec.LQ[r][j] = 0.f;
     KV_UNROLL for (int j = 0; j < N; ++j) ec.invdQ[j] = 0.f;
   }
-  typename view_of<MEM, N, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, TP);
+  typename view_of<MEM, L, R, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, TP);
 
   // state carried over iterations
   ElboStep<C> es;                    // sample at t
@@ -360,8 +347,8 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, float*
       load_row<R>(a.mu_p + (bt + 1) * N + row0, mp1);
       float J[R][N], LU[R][N], invu[N];
       ok = smoother_gain<C>(g, T0, T1, Sf, A1, Sp1, J, LU, invu) && ok;        // A1_v in T0, LU_v in T1
-      typename view_of<MEM, N, N>::type A1_v, LU_v;
-      if constexpr (MEM) { A1_v = MemView<N, N>{T0}; LU_v = MemView<N, N>{T1}; }
+      typename view_of<MEM, L, R, N>::type A1_v, LU_v;
+      if constexpr (MEM) { A1_v = MemView<L, R, N>{T0.p, T0.g}; LU_v = MemView<L, R, N>{T1.p, T1.g}; }
       else { A1_v = RegView<N, N>{A1}; LU_v = RegView<N, N>{LU}; }
       float D[R][N], d_own[R], d[N];
       KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -470,15 +457,12 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, float*
 // sweep 4: filter adjoint (A.5) + mixing adjoint (A.0), backward in time
 // ---------------------------------------------------------------------------------------
 template <class C>
-KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, float* tiles, const Group<C::L, C::R>& g,
+KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const BTiles<C>& tl, const Group<C::L, C::R>& g,
                       int b, bool active, GradAcc<C>& acc) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L, K = C::K;
   constexpr bool MEM = C::MEM;
-  using BT = BTiles<C>;
-  float* T0 = tiles + BT::oT(0); float* T1 = tiles + BT::oT(1); float* T2 = tiles + BT::oT(2);
-  float* T3 = tiles + BT::oT(3); float* T4 = tiles + BT::oT(4); float* T5 = tiles + BT::oT(5);
-  float* CB = tiles + BT::oC; float* KB = tiles + BT::oK; float* PB = tiles + BT::oP;
-  float* VB = tiles + BT::oV;
+  const TileRef T0 = tl.nn(0), T1 = tl.nn(1), T2 = tl.nn(2), T3 = tl.nn(3), T4 = tl.nn(4), T5 = tl.nn(5);
+  const TileRef CB = tl.np(0), KB = tl.np(1), PB = tl.np(2), VB = tl.vec(0);
   const int row0 = g.row0();
   const int T = a.T;
   bool ok = true;

@@ -10,7 +10,7 @@ namespace kvae {
 
 // own rows of sym(X) (+ jitter on the diagonal)
 template <class C>
-KV_FN void sym_jitter_rows(const Group<C::L, C::R>& g, const float (&X)[C::R][C::N], float* buf, float jitter,
+KV_FN void sym_jitter_rows(const Group<C::L, C::R>& g, const float (&X)[C::R][C::N], TileRef buf, float jitter,
                            float (&out)[C::R][C::N]) {
   constexpr int N = C::N, R = C::R;
   auto X_v = publish<C::MEM, C::L, R, N>(g, X, buf);
@@ -34,7 +34,7 @@ template <class C> struct ElboConst {
 };
 
 template <class C>
-KV_FN bool elbo_const(const Group<C::L, C::R>& g, const float* base, float* xbuf, float jitter, ElboConst<C>& ec) {
+KV_FN bool elbo_const(const Group<C::L, C::R>& g, const float* base, TileRef xbuf, float jitter, ElboConst<C>& ec) {
   constexpr int N = C::N, P = C::P, R = C::R;
   bool ok = true;
   float Rm[P][P];
@@ -63,7 +63,7 @@ template <class C> struct ElboStep {
 
 // z_t for one step: loads Sigma_s / mu_s at index bt (xbuf: [N x N] tile, vbuf: N-vector slot)
 template <class C>
-KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, float* xbuf, float* vbuf, long bt, float jitter,
+KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, long bt, float jitter,
                          const float (&eps)[C::N], ElboStep<C>& es) {
   constexpr int N = C::N, R = C::R;
   const int row0 = g.row0();
@@ -83,16 +83,15 @@ KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, float* xbuf,
 
 // acc: [0] transition  [1] emission  [2] init  [3] entropy  [4] sum(mask)
 template <class C>
-KV_FN void elbo_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
                       float jitter, double (&acc)[5]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
-  using TL = Tiles<C>;
   const int row0 = g.row0();
   const int T = a.T;
   ElboConst<C> ec;
-  bool ok = elbo_const<C>(g, base, tiles + TL::oX0, jitter, ec);
-  typename view_of<MEM, N, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, tiles + TL::oXP);
+  bool ok = elbo_const<C>(g, base, tl.nn(0), jitter, ec);
+  typename view_of<MEM, L, R, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, tl.nn(3));
   float zprev[N];
   KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = 0.f;
   double s_tr = 0.0, s_em = 0.0, s_in = 0.0, s_en = 0.0, s_m = 0.0;
@@ -104,7 +103,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, float* tiles, const Grou
     float eps[N];
     load_row<N>(a.eps + bt * N, eps);
     ElboStep<C> es;
-    ok = elbo_sample_t<C>(a, g, tiles + TL::oX0, tiles + TL::oV, bt, jitter, eps, es) && ok;
+    ok = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), bt, jitter, eps, es) && ok;
 
     // entropy = -log N(z; mu_s, Ls Ls^T) = 1/2 |eps|^2 + sum log Ls_ii + n/2 log 2pi            (:389)
     float e2 = 0.f;
@@ -116,7 +115,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, float* tiles, const Grou
       float S0[R][N], L0[R][N], invd0[N], dg0[R];
       copy_rows<C, N>(base + Base<C>::oS0, row0, S0);
       ok = chol_dist<L, R>(g, S0, L0, invd0, dg0) && ok;
-      auto L0_v = publish<MEM, L, R, N>(g, L0, tiles + TL::oX1);
+      auto L0_v = publish<MEM, L, R, N>(g, L0, tl.nn(1));
       float w[N];
       KV_UNROLL for (int j = 0; j < N; ++j) w[j] = es.z[j] - base[Base<C>::oMu0 + j];
       solve_vec_l<N>(w, L0_v, invd0);
@@ -135,14 +134,14 @@ KV_FN void elbo_sweep(const Args& a, const float* base, float* tiles, const Grou
         KV_UNROLL for (int j = 0; j < M; ++j) s2 = fmaf(Bm[r][j], in.u[j], s2);
         x_own[r] = es.z_own[r] - (s1 + s2);
       }
-      allgather<MEM, L, R>(g, x_own, tiles + TL::oV2, x);
+      allgather<MEM, L, R>(g, x_own, tl.vec(1), x);
       float q = 0.f, ld;
       if constexpr (C::QPM) {
         float Q[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
         mix_Q<C>(base, in.al, row0, Q);
-        sym_jitter_rows<C>(g, Q, tiles + TL::oX1, jitter, Qs);
+        sym_jitter_rows<C>(g, Q, tl.nn(1), jitter, Qs);
         ok = chol_dist<L, R>(g, Qs, LQ, invdQ, dgQ) && ok;
-        auto LQ_v = publish<MEM, L, R, N>(g, LQ, tiles + TL::oX2);
+        auto LQ_v = publish<MEM, L, R, N>(g, LQ, tl.nn(2));
         solve_vec_l<N>(x, LQ_v, invdQ);
         ld = logdet_half<C>(g, dgQ);
       } else {

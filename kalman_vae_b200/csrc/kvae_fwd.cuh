@@ -66,20 +66,8 @@ KV_FN void base_fill(float* base, int i, const float* A, const float* Bm, const 
   base[i] = v;
 }
 
-// Per-group scratch tiles (only used when C::MEM).
-template <class C> struct Tiles {
-  static constexpr int szNN = pad4(C::N * ld_of<C::N>::v);
-  static constexpr int szNP = pad4(C::N * ld_of<C::P>::v);
-  static constexpr int oX0 = 0;
-  static constexpr int oX1 = oX0 + szNN;
-  static constexpr int oX2 = oX1 + szNN;
-  static constexpr int oXP = oX2 + szNN;  // persistent tile (e.g. chol of a constant Q)
-  static constexpr int oC = oXP + szNN;
-  static constexpr int oK = oC + szNP;
-  static constexpr int oV = oK + szNP;   // vector all-gather slots (N floats each)
-  static constexpr int oV2 = oV + pad4(C::N);
-  static constexpr int total = C::MEM ? (oV2 + pad4(C::N)) : 0;
-};
+// Per-warp scratch tiles of the forward / ELBO kernels: 4 [n x n] + 2 [n x p] + 2 vector slots.
+template <class C> using FTiles = TileSet<C::L, C::R, C::P, 4, 2, 2, C::MEM>;
 
 // ---------------------------------------------------------------------------------------
 // per-step inputs
@@ -181,13 +169,11 @@ KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)
 // sweep 1: filter.  On return Sig (own rows) and mu (replicated) hold the last filtered belief.
 // ---------------------------------------------------------------------------------------
 template <class C>
-KV_FN void filter_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
                         float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
-  using TL = Tiles<C>;
-  float* X0 = tiles + TL::oX0; float* X1 = tiles + TL::oX1; float* X2 = tiles + TL::oX2;
-  float* CB = tiles + TL::oC; float* KB = tiles + TL::oK; float* VB = tiles + TL::oV;
+  const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), CB = tl.np(0), KB = tl.np(1), VB = tl.vec(0);
   const int row0 = g.row0();
   const int T = a.T;
   bool ok = true;
@@ -304,7 +290,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, float* tiles, const Gr
 // factor and XL holds its published copy.
 // ---------------------------------------------------------------------------------------
 template <class C>
-KV_FN bool smoother_gain(const Group<C::L, C::R>& g, float* XA, float* XL, const float (&Sf)[C::R][C::N],
+KV_FN bool smoother_gain(const Group<C::L, C::R>& g, TileRef XA, TileRef XL, const float (&Sf)[C::R][C::N],
                          const float (&A1)[C::R][C::N], const float (&Sp1)[C::R][C::N], float (&J)[C::R][C::N],
                          float (&LU)[C::R][C::N], float (&invu)[C::N]) {
   constexpr int N = C::N, R = C::R, L = C::L;
@@ -322,12 +308,11 @@ KV_FN bool smoother_gain(const Group<C::L, C::R>& g, float* XA, float* XL, const
 // belief (= smoothed belief at T-1).
 // ---------------------------------------------------------------------------------------
 template <class C>
-KV_FN void smoother_sweep(const Args& a, const float* base, float* tiles, const Group<C::L, C::R>& g, int b, bool active,
+KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
                           float (&Sig)[C::R][C::N], float (&mus)[C::R]) {
   constexpr int N = C::N, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
-  using TL = Tiles<C>;
-  float* X0 = tiles + TL::oX0; float* X1 = tiles + TL::oX1; float* X2 = tiles + TL::oX2; float* VB = tiles + TL::oV;
+  const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), VB = tl.vec(0);
   const int row0 = g.row0();
   const int T = a.T;
   bool ok = true;

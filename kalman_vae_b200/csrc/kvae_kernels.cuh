@@ -19,7 +19,11 @@ template <class C> __device__ __forceinline__ float* stage_base(float* smem, con
 }
 
 template <class C> constexpr size_t smem_bytes() {
-  return sizeof(float) * (size_t)(Base<C>::total + (kThreads / C::L) * Tiles<C>::total);
+  return sizeof(float) * (size_t)(Base<C>::total + (kThreads / 32) * FTiles<C>::warp_total);
+}
+// this thread's tile set: per-warp region + group index inside the warp
+template <class TS> __device__ __forceinline__ TS warp_tiles(float* tiles_all, int L) {
+  return TS{tiles_all + (threadIdx.x >> 5) * TS::warp_total, (int)((threadIdx.x & 31) / L)};
 }
 
 template <class C>
@@ -33,10 +37,10 @@ __global__ void __launch_bounds__(kThreads) k_filter_smooth(Args a, BasePtrs bp,
   int b = blockIdx.x * GPB + gi;
   const bool active = b < a.B;
   if (!active) b = a.B - 1;  // tail groups recompute the last sequence and store nothing
-  float* tiles = tiles_all + gi * Tiles<C>::total;
+  const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
   float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
-  filter_sweep<C>(a, base, tiles, g, b, active, Sig, mu, mu_own);
-  if (smooth) smoother_sweep<C>(a, base, tiles, g, b, active, Sig, mu_own);
+  filter_sweep<C>(a, base, tl, g, b, active, Sig, mu, mu_own);
+  if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, Sig, mu_own);
 }
 
 template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth, cudaStream_t s) {
@@ -70,9 +74,9 @@ __global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float ji
   int b = blockIdx.x * GPB + gi;
   const bool active = b < a.B;
   if (!active) b = a.B - 1;
-  float* tiles = tiles_all + gi * Tiles<C>::total;
+  const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  elbo_sweep<C>(a, base, tiles, g, b, active, jitter, acc);
+  elbo_sweep<C>(a, base, tl, g, b, active, jitter, acc);
   // block reduction (fixed order -> deterministic)
   __shared__ double red[kThreads / 32][5];
 #pragma unroll
@@ -92,21 +96,22 @@ __global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float ji
 }
 
 // terms: [0] trans [1] emiss [2] init [3] entropy [4] sum(mask) [5] elbo [6] 1/max(sum mask,1) [7] 0
+// one warp per sum, lanes stride over the per-CTA partials, fixed shuffle tree -> deterministic
 static __global__ void k_elbo_final(const double* __restrict__ partials, int nblocks, float* __restrict__ terms) {
-  __shared__ double red[256][5];
-  double v[5] = {0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
-    for (int j = 0; j < 5; ++j) v[j] += partials[(size_t)i * 5 + j];
-  for (int j = 0; j < 5; ++j) red[threadIdx.x][j] = v[j];
-  __syncthreads();
-  for (int s = blockDim.x / 2; s >= 1; s >>= 1) {
-    if ((int)threadIdx.x < s) for (int j = 0; j < 5; ++j) red[threadIdx.x][j] += red[threadIdx.x + s][j];
-    __syncthreads();
+  __shared__ double tot[5];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 5) {
+    double v = 0.0;
+    for (int i = lane; i < nblocks; i += 32) v += partials[(size_t)i * 5 + w];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) tot[w] = v;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const double n = red[0][4] < 1.0 ? 1.0 : red[0][4];
-    for (int j = 0; j < 5; ++j) terms[j] = (float)red[0][j];
-    terms[5] = (float)((red[0][0] + red[0][1] + red[0][2] + red[0][3]) / n);
+    const double n = tot[4] < 1.0 ? 1.0 : tot[4];
+    for (int j = 0; j < 5; ++j) terms[j] = (float)tot[j];
+    terms[5] = (float)((tot[0] + tot[1] + tot[2] + tot[3]) / n);
     terms[6] = (float)(1.0 / n);
     terms[7] = 0.f;
   }
@@ -130,7 +135,7 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
   k_elbo<C><<<grid, kThreads, sm, s>>>(a, bp, jitter, reinterpret_cast<double*>(ws));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  k_elbo_final<<<1, 256, 0, s>>>(reinterpret_cast<const double*>(ws), grid, terms);
+  k_elbo_final<<<1, 160, 0, s>>>(reinterpret_cast<const double*>(ws), grid, terms);
   return (int)cudaGetLastError();
 }
 
@@ -141,7 +146,7 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
 struct GradPtrs { float *dA, *dB, *dC, *dQ; };
 
 template <class C> constexpr size_t smem_floats_bwd() {
-  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(kThreads / C::L) * BTiles<C>::total;
+  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(kThreads / 32) * BTiles<C>::warp_total;
   constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
   return tiles > red ? tiles : red;
 }
@@ -158,12 +163,12 @@ __global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp
   int b = blockIdx.x * GPB + gi;
   const bool active = b < a.B;
   if (!active) b = a.B - 1;
-  float* tiles = tiles_all + gi * BTiles<C>::total;
+  const BTiles<C> tl = warp_tiles<BTiles<C>>(tiles_all, C::L);
   w.c_elbo = g_elbo ? (*g_elbo) * terms[6] : 0.f;
   GradAcc<C> acc;
   acc.zero();
-  bwd_sweep3<C>(a, w, base, tiles, g, b, active, acc);
-  bwd_sweep4<C>(a, w, base, tiles, g, b, active, acc);
+  bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
+  bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
   if (!active) acc.zero();
   // reduce over the groups of a warp (xor over the group-index bits of the lane id)
 #pragma unroll
@@ -184,13 +189,18 @@ __global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp
   for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) partials[(size_t)blockIdx.x * GradAcc<C>::PSZ + i] = red[i];
 }
 
-// sums the per-CTA partials (double accumulation) and scatters into dA | dB | dC | dQ
+// sums the per-CTA partials and scatters into dA | dB | dC | dQ: one warp per parameter element, lanes
+// stride over the CTAs, fp64 accumulation, fixed shuffle tree -> deterministic
 static __global__ void k_param_final(const float* __restrict__ partials, int nblocks, int psz, int nA, int nB, int nC,
-                              GradPtrs gp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                     GradPtrs gp) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= psz) return;
   double v = 0.0;
-  for (int blk = 0; blk < nblocks; ++blk) v += (double)partials[(size_t)blk * psz + i];
+  for (int blk = lane; blk < nblocks; blk += 32) v += (double)partials[(size_t)blk * psz + i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane != 0) return;
   const float f = (float)v;
   if (i < nA) gp.dA[i] = f;
   else if (i < nA + nB) gp.dB[i - nA] = f;
@@ -232,7 +242,7 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   constexpr int psz = GradAcc<C>::PSZ;
-  k_param_final<<<(psz + 127) / 128, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
+  k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
                                                   C::K * C::P * C::N, gp);
   return (int)cudaGetLastError();
 }

@@ -124,13 +124,50 @@ template <int L, int R> struct Group {
 };
 
 // ---------------------------------------------------------------------------------------
+// Shared-memory tile geometry.  Tiles are allocated per WARP (G = 32/L groups each).
+//   * n = 4, L = 4 (eight sequences per warp, rows of <= 4 floats): rows of the eight groups are
+//     interleaved and rotated, element (r,c) of group g at  r*(G*COLS) + ((g + 2r) mod G)*COLS + c.
+//     Row publishes (128-bit, one row per lane), broadcast row reads and the scalar transposed reads
+//     at(k, lane) are then all bank-conflict free.
+//   * otherwise: group-major, padded row stride, group stride padded to == L (mod 32) floats so that
+//     the groups of a warp start in different banks.
+// ---------------------------------------------------------------------------------------
+struct TileRef { float* p; int g; };
+
+constexpr int pad_res(int x, int L) {  // smallest y >= x, y % 4 == 0, y % 32 == max(L,4) % 32 (L > 1)
+  int y = (x + 3) & ~3;
+  if (L > 1) { const int want = (L < 4 ? 4 : L) % 32; while (y % 32 != want) y += 4; }
+  return y;
+}
+template <int L, int R, int COLS> struct TileGeom {
+  static constexpr int ROWS = L * R;
+  static constexpr int G = (L == 1) ? 1 : 32 / L;
+  static constexpr bool INTER = (L == 4) && (R == 1) && (COLS <= 4);
+  static constexpr int LD = INTER ? G * COLS : ld_of<COLS>::v;
+  static constexpr int group_floats = INTER ? ROWS * COLS : pad_res(ROWS * ld_of<COLS>::v, L);
+  static constexpr int warp_floats = group_floats * G;
+  // offset of row r of group g inside the tile whose TileRef.p is used (p already includes the
+  // group offset for the group-major layout)
+  static KV_FN int row_off(int g, int r) {
+    if constexpr (INTER) return r * LD + ((g + 2 * r) & (G - 1)) * COLS;
+    else { (void)g; return r * LD; }
+  }
+};
+template <int L, int R> struct VecGeom {  // replicated n-vector slot per group
+  static constexpr int G = (L == 1) ? 1 : 32 / L;
+  static constexpr int group_floats = (L * R + 3) & ~3;
+  static constexpr int warp_floats = group_floats * G;
+};
+
+// ---------------------------------------------------------------------------------------
 // Fully visible matrix views
 // ---------------------------------------------------------------------------------------
-template <int ROWS, int COLS> struct MemView {  // tile in shared (or host) memory
-  static constexpr int LD = ld_of<COLS>::v;
+template <int L, int R, int COLS> struct MemView {  // tile in shared (or host) memory
+  using Geo = TileGeom<L, R, COLS>;
   const float* p;
-  KV_FN float at(int r, int c) const { return p[r * LD + c]; }
-  KV_FN void row(int r, float (&o)[COLS]) const { load_row<COLS>(p + r * LD, o); }
+  int g;
+  KV_FN float at(int r, int c) const { return p[Geo::row_off(g, r) + c]; }
+  KV_FN void row(int r, float (&o)[COLS]) const { load_row<COLS>(p + Geo::row_off(g, r), o); }
 };
 template <int ROWS, int COLS> struct RegView {  // alias of a register array (L == 1)
   const float (*v)[COLS];
@@ -139,19 +176,19 @@ template <int ROWS, int COLS> struct RegView {  // alias of a register array (L 
     KV_UNROLL for (int c = 0; c < COLS; ++c) o[c] = v[r][c];
   }
 };
-template <bool MEM, int ROWS, int COLS> struct view_of { using type = RegView<ROWS, COLS>; };
-template <int ROWS, int COLS> struct view_of<true, ROWS, COLS> { using type = MemView<ROWS, COLS>; };
+template <bool MEM, int L, int R, int COLS> struct view_of { using type = RegView<L * R, COLS>; };
+template <int L, int R, int COLS> struct view_of<true, L, R, COLS> { using type = MemView<L, R, COLS>; };
 
 // publish the lane's R rows of an [L*R x COLS] matrix; returns the full view.
 // For RegView the view ALIASES x: x must stay unmodified while the view is in use.
 template <bool MEM, int L, int R, int COLS>
-KV_FN typename view_of<MEM, L * R, COLS>::type publish(const Group<L, R>& g, const float (&x)[R][COLS], float* buf) {
+KV_FN typename view_of<MEM, L, R, COLS>::type publish(const Group<L, R>& g, const float (&x)[R][COLS], TileRef buf) {
   if constexpr (MEM) {
-    constexpr int LD = ld_of<COLS>::v;
+    using Geo = TileGeom<L, R, COLS>;
     g.sync();  // everyone finished reading the previous contents of buf
-    KV_UNROLL for (int r = 0; r < R; ++r) store_row<COLS>(buf + (g.row0() + r) * LD, x[r]);
+    KV_UNROLL for (int r = 0; r < R; ++r) store_row<COLS>(buf.p + Geo::row_off(buf.g, g.row0() + r), x[r]);
     g.sync();
-    return MemView<L * R, COLS>{buf};
+    return MemView<L, R, COLS>{buf.p, buf.g};
   } else {
     (void)g; (void)buf;
     return RegView<L * R, COLS>{x};
@@ -160,17 +197,33 @@ KV_FN typename view_of<MEM, L * R, COLS>::type publish(const Group<L, R>& g, con
 
 // all-gather of a distributed n-vector (lane holds R entries) into a replicated one
 template <bool MEM, int L, int R>
-KV_FN void allgather(const Group<L, R>& g, const float (&x)[R], float* vbuf, float (&full)[L * R]) {
+KV_FN void allgather(const Group<L, R>& g, const float (&x)[R], TileRef vbuf, float (&full)[L * R]) {
   if constexpr (MEM) {
     g.sync();
-    KV_UNROLL for (int r = 0; r < R; ++r) vbuf[g.row0() + r] = x[r];
+    KV_UNROLL for (int r = 0; r < R; ++r) vbuf.p[g.row0() + r] = x[r];
     g.sync();
-    load_row<L * R>(vbuf, full);
+    load_row<L * R>(vbuf.p, full);
   } else {
     (void)g; (void)vbuf;
     KV_UNROLL for (int r = 0; r < R; ++r) full[r] = x[r];
   }
 }
+
+// The tiles of one warp: NNN [n x n] tiles, NNP [n x p] tiles, NV vector slots.
+template <int L, int R, int P, int NNN, int NNP, int NV, bool MEM> struct TileSet {
+  using GNN = TileGeom<L, R, L * R>;
+  using GNP = TileGeom<L, R, P>;
+  using GV = VecGeom<L, R>;
+  static constexpr int oNP = NNN * GNN::warp_floats;
+  static constexpr int oV = oNP + NNP * GNP::warp_floats;
+  static constexpr int warp_total = MEM ? (oV + NV * GV::warp_floats) : 0;
+  static constexpr int groups_per_warp = GNN::G;
+  float* base;  // this warp's region
+  int g;        // group index inside the warp
+  KV_FN TileRef nn(int i) const { return TileRef{base + i * GNN::warp_floats + (GNN::INTER ? 0 : g * GNN::group_floats), g}; }
+  KV_FN TileRef np(int i) const { return TileRef{base + oNP + i * GNP::warp_floats + (GNP::INTER ? 0 : g * GNP::group_floats), g}; }
+  KV_FN TileRef vec(int i) const { return TileRef{base + oV + i * GV::warp_floats + g * GV::group_floats, g}; }
+};
 
 // ---------------------------------------------------------------------------------------
 // products.  X: local rows; Y / Xv: fully visible views.

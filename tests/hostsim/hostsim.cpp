@@ -15,12 +15,13 @@ struct HostParams { const float *A, *Bm, *C, *Q, *R, *mu0, *S0; };
 template <class C> static void run_fwd(const Args& a, const HostParams& hp, int smooth) {
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
-  std::vector<float> tiles(Tiles<C>::total + 4);
+  std::vector<float> tiles(FTiles<C>::warp_total + 4);
   Group<C::L, C::R> g{0};
+  FTiles<C> tl{tiles.data(), 0};
   for (int b = 0; b < a.B; ++b) {
     float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
-    filter_sweep<C>(a, base.data(), tiles.data(), g, b, true, Sig, mu, mu_own);
-    if (smooth) smoother_sweep<C>(a, base.data(), tiles.data(), g, b, true, Sig, mu_own);
+    filter_sweep<C>(a, base.data(), tl, g, b, true, Sig, mu, mu_own);
+    if (smooth) smoother_sweep<C>(a, base.data(), tl, g, b, true, Sig, mu_own);
   }
 }
 
@@ -51,10 +52,11 @@ extern "C" int hostsim_fwd(int N, int P, int M, int K, int switching, int force_
 template <class C> static void run_elbo(const Args& a, const HostParams& hp, float jitter, double* acc5) {
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
-  std::vector<float> tiles(Tiles<C>::total + 4);
+  std::vector<float> tiles(FTiles<C>::warp_total + 4);
   Group<C::L, C::R> g{0};
+  FTiles<C> tl{tiles.data(), 0};
   double acc[5] = {0, 0, 0, 0, 0};
-  for (int b = 0; b < a.B; ++b) elbo_sweep<C>(a, base.data(), tiles.data(), g, b, true, jitter, acc);
+  for (int b = 0; b < a.B; ++b) elbo_sweep<C>(a, base.data(), tl, g, b, true, jitter, acc);
   for (int i = 0; i < 5; ++i) acc5[i] = acc[i];
 }
 
@@ -83,7 +85,8 @@ extern "C" int hostsim_elbo(int N, int P, int M, int K, int switching, int force
 template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParams& hp, double* gp, float** dbg) {
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
-  std::vector<float> tiles(BTiles<C>::total + 4);
+  std::vector<float> tiles(BTiles<C>::warp_total + 4);
+  BTiles<C> tl{tiles.data(), 0};
   const size_t nn = (size_t)a.B * a.T * C::N * C::N, nv = (size_t)a.B * a.T * C::N;
   std::vector<float> wSf(nn), wSp(nn), wmf(nv), wmp(nv);
   w.w_Sig_f = wSf.data(); w.w_Sig_p = wSp.data(); w.w_mu_f = wmf.data(); w.w_mu_p = wmp.data();
@@ -92,8 +95,8 @@ template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParam
   for (int b = 0; b < a.B; ++b) {
     GradAcc<C> acc;
     acc.zero();
-    bwd_sweep3<C>(a, w, base.data(), tiles.data(), g, b, true, acc);
-    bwd_sweep4<C>(a, w, base.data(), tiles.data(), g, b, true, acc);
+    bwd_sweep3<C>(a, w, base.data(), tl, g, b, true, acc);
+    bwd_sweep4<C>(a, w, base.data(), tl, g, b, true, acc);
     acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
   }
   if (dbg) {
