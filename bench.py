@@ -281,10 +281,10 @@ def run_cuda(args, rank, local_rank, world):
             if world > 1:
                 from kalman_vae_b200.dist import allreduce_param_grads
                 allreduce_param_grads(list(grads[2:]))
-            flat = torch.cat([val.reshape(1)] + [g.reshape(-1) for g in grads[2:]])
+            flat = torch.cat([val.detach().reshape(1)] + [g.reshape(-1) for g in grads[2:]])
             out_host.copy_(flat, non_blocking=True)
 
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 20)):   # lets the caching allocator reach its steady state
             e2e_step()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

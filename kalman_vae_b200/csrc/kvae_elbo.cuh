@@ -81,10 +81,13 @@ KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf
   return ok;
 }
 
-// acc: [0] transition  [1] emission  [2] init  [3] entropy  [4] sum(mask)
+// ELBO terms of time steps [t0, t1) of sequence b (the steps are independent given z_{t0-1}, which is
+// recomputed at the chunk start, so a sequence can be cut into chunks owned by different lane groups).
+// acc: [0] transition  [1] emission  [2] init  [3] entropy  [4] sum(mask).  zbuf (nullable): z_t is stored
+// there ([B,T,N]) for the adjoint.
 template <class C>
 KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
-                      float jitter, double (&acc)[5]) {
+                      float jitter, int t0, int t1, float* zbuf, double (&acc)[5]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
   const int row0 = g.row0();
@@ -95,8 +98,16 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
   float zprev[N];
   KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = 0.f;
   double s_tr = 0.0, s_em = 0.0, s_in = 0.0, s_en = 0.0, s_m = 0.0;
+  if (t0 > 0) {
+    const long btp = (long)b * T + (t0 - 1);
+    float epsp[N];
+    load_row<N>(a.eps + btp * N, epsp);
+    ElboStep<C> esp;
+    ok = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), btp, jitter, epsp, esp) && ok;
+    KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = esp.z[j];
+  }
 
-  for (int t = 0; t < T; ++t) {
+  for (int t = t0; t < t1; ++t) {
     const long bt = (long)b * T + t;
     StepIn<C> in;
     load_step<C>(a, bt, in);
@@ -104,6 +115,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
     load_row<N>(a.eps + bt * N, eps);
     ElboStep<C> es;
     ok = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), bt, jitter, eps, es) && ok;
+    if (zbuf && active) store_row<R>(zbuf + bt * N + row0, es.z_own);
 
     // entropy = -log N(z; mu_s, Ls Ls^T) = 1/2 |eps|^2 + sum log Ls_ii + n/2 log 2pi            (:389)
     float e2 = 0.f;

@@ -18,6 +18,12 @@ template <class C> __device__ __forceinline__ float* stage_base(float* smem, con
   return smem + Base<C>::total;
 }
 
+template <class C> __device__ __forceinline__ Group<C::L, C::R> this_group() {
+  // every kernel keeps the control flow of all groups of a warp identical (CTA-uniform time chunks, tail
+  // groups mirror a valid sequence), so the group collectives can name the whole warp: sub-warp masks are
+  // legal too but let the hardware split the warp, which costs ~15-40 % here (measured)
+  return Group<C::L, C::R>{(int)(threadIdx.x % C::L), 0xffffffffu};
+}
 template <class C> constexpr size_t smem_bytes() {
   return sizeof(float) * (size_t)(Base<C>::total + (kThreads / 32) * FTiles<C>::warp_total);
 }
@@ -33,7 +39,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_smooth(Args a, BasePtrs bp,
   float* tiles_all = stage_base<C>(base, bp);
   constexpr int GPB = kThreads / C::L;
   const int gi = threadIdx.x / C::L;
-  Group<C::L, C::R> g{(int)(threadIdx.x % C::L)};
+  const Group<C::L, C::R> g = this_group<C>();
   int b = blockIdx.x * GPB + gi;
   const bool active = b < a.B;
   if (!active) b = a.B - 1;  // tail groups recompute the last sequence and store nothing
@@ -63,20 +69,49 @@ template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth,
 // ------------------------------------------------------------------------------------------------
 template <class C> constexpr size_t smem_bytes_elbo() { return smem_bytes<C>(); }
 
+// Time-parallel kernels cut every sequence into `chunks` pieces of TC = ceil(T/chunks) steps so that small
+// batches still give each SM sub-partition several warps (>= ~6); long chunks keep the per-chunk overhead
+// (one or two extra Cholesky factorisations at the chunk start) small.
+inline int pick_chunks(int B, int T, int L) {
+  const long want_groups = 148L * 4 * 6 * (32 / L);
+  long ch = (want_groups + B - 1) / B;
+  const long max_ch = T >= 8 ? T / 4 : 1;
+  if (ch > max_ch) ch = max_ch;
+  if (ch < 1) ch = 1;
+  return (int)ch;
+}
+struct ChunkMap { int chunks, tc; };
+inline ChunkMap make_chunks(int B, int T, int L) {
+  ChunkMap cm;
+  cm.chunks = pick_chunks(B, T, L);
+  cm.tc = (T + cm.chunks - 1) / cm.chunks;
+  cm.chunks = (T + cm.tc - 1) / cm.tc;   // no empty chunk
+  return cm;
+}
+// CTA -> (chunk, block of sequences): every group of a CTA works on the SAME time chunk of different
+// sequences, so control flow stays warp-uniform; inactive tail groups mirror the last sequence, store nothing
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float jitter, double* __restrict__ partials) {
+__device__ __forceinline__ bool chunk_of(const Args& a, ChunkMap cm, int& b, int& t0, int& t1) {
+  constexpr int GPB = kThreads / C::L;
+  const int c = blockIdx.x % cm.chunks;
+  b = (blockIdx.x / cm.chunks) * GPB + threadIdx.x / C::L;
+  const bool active = b < a.B;
+  if (!active) b = a.B - 1;
+  t0 = c * cm.tc;
+  t1 = t0 + cm.tc < a.T ? t0 + cm.tc : a.T;
+  return active && t0 < a.T;
+}
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float jitter, ChunkMap cm, double* __restrict__ partials) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
-  constexpr int GPB = kThreads / C::L;
-  const int gi = threadIdx.x / C::L;
-  Group<C::L, C::R> g{(int)(threadIdx.x % C::L)};
-  int b = blockIdx.x * GPB + gi;
-  const bool active = b < a.B;
-  if (!active) b = a.B - 1;
+  const Group<C::L, C::R> g = this_group<C>();
+  int b, t0, t1;
+  const bool active = chunk_of<C>(a, cm, b, t0, t1);
   const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  elbo_sweep<C>(a, base, tl, g, b, active, jitter, acc);
+  elbo_sweep<C>(a, base, tl, g, b, active, jitter, t0, t1, nullptr, acc);
   // block reduction (fixed order -> deterministic)
   __shared__ double red[kThreads / 32][5];
 #pragma unroll
@@ -117,9 +152,12 @@ static __global__ void k_elbo_final(const double* __restrict__ partials, int nbl
   }
 }
 
-template <class C> size_t elbo_ws_bytes(int B) {
+template <class C> int chunk_grid(int B, int chunks) {
   constexpr int GPB = kThreads / C::L;
-  return sizeof(double) * 5 * (size_t)((B + GPB - 1) / GPB);
+  return ((B + GPB - 1) / GPB) * chunks;
+}
+template <class C> size_t elbo_ws_bytes(int B, int T) {
+  return sizeof(double) * 5 * (size_t)chunk_grid<C>(B, make_chunks(B, T, C::L).chunks);
 }
 
 template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitter, float* terms, void* ws, cudaStream_t s) {
@@ -131,8 +169,9 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int grid = (a.B + GPB - 1) / GPB;
-  k_elbo<C><<<grid, kThreads, sm, s>>>(a, bp, jitter, reinterpret_cast<double*>(ws));
+  const ChunkMap cm = make_chunks(a.B, a.T, C::L);
+  const int grid = chunk_grid<C>(a.B, cm.chunks);
+  k_elbo<C><<<grid, kThreads, sm, s>>>(a, bp, jitter, cm, reinterpret_cast<double*>(ws));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   k_elbo_final<<<1, 160, 0, s>>>(reinterpret_cast<const double*>(ws), grid, terms);
@@ -151,6 +190,28 @@ template <class C> constexpr size_t smem_floats_bwd() {
   return tiles > red ? tiles : red;
 }
 
+// CTA reduction of the per-lane parameter-gradient accumulators in a fixed order (deterministic):
+// groups of a warp by xor-shuffles, warps through shared memory, one partial row per CTA.
+template <class C>
+__device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L, C::R>& g, bool active, float* red,
+                                               float* __restrict__ partial_row) {
+  if (!active) acc.zero();
+#pragma unroll
+  for (int off = C::L; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
+  }
+  __syncthreads();   // tiles are dead: reuse them
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int wq = 0; wq < kThreads / 32; ++wq) {
+    if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) partial_row[i] = red[i];
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
                                                   const float* __restrict__ terms, float* __restrict__ partials) {
@@ -159,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp
   float* tiles_all = stage_base<C>(base, bp);
   constexpr int GPB = kThreads / C::L;
   const int gi = threadIdx.x / C::L;
-  Group<C::L, C::R> g{(int)(threadIdx.x % C::L)};
+  const Group<C::L, C::R> g = this_group<C>();
   int b = blockIdx.x * GPB + gi;
   const bool active = b < a.B;
   if (!active) b = a.B - 1;
@@ -169,24 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp
   acc.zero();
   bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
   bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
-  if (!active) acc.zero();
-  // reduce over the groups of a warp (xor over the group-index bits of the lane id)
-#pragma unroll
-  for (int off = C::L; off < 32; off <<= 1) {
-#pragma unroll
-    for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
-  }
-  // then over the warps of the CTA in fixed order, through shared memory (tiles are dead now)
-  float* red = tiles_all;
-  __syncthreads();
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) red[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int wq = 0; wq < kThreads / 32; ++wq) {
-    if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) partials[(size_t)blockIdx.x * GradAcc<C>::PSZ + i] = red[i];
+  cta_reduce_acc<C>(acc, g, active, tiles_all, partials + (size_t)blockIdx.x * GradAcc<C>::PSZ);
 }
 
 // sums the per-CTA partials and scatters into dA | dB | dC | dQ: one warp per parameter element, lanes
@@ -214,8 +258,8 @@ template <class C> size_t bwd_ws_bytes(int B, int T) {
   constexpr int GPB = kThreads / C::L;
   const size_t nn = align256(sizeof(float) * (size_t)B * T * C::N * C::N);
   const size_t nv = align256(sizeof(float) * (size_t)B * T * C::N);
-  const size_t np = align256(sizeof(float) * (size_t)((B + GPB - 1) / GPB) * GradAcc<C>::PSZ);
-  return 2 * nn + 2 * nv + np;
+  const size_t rows = (size_t)((B + GPB - 1) / GPB);
+  return 2 * nn + 2 * nv + align256(sizeof(float) * rows * GradAcc<C>::PSZ);
 }
 
 template <class C>
@@ -237,13 +281,13 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   w.w_mu_f = reinterpret_cast<float*>(p); p += nv;
   w.w_mu_p = reinterpret_cast<float*>(p); p += nv;
   float* partials = reinterpret_cast<float*>(p);
+  constexpr int psz = GradAcc<C>::PSZ;
   const int grid = (a.B + GPB - 1) / GPB;
   k_bwd<C><<<grid, kThreads, sm, s>>>(a, w, bp, g_elbo, terms, partials);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  constexpr int psz = GradAcc<C>::PSZ;
   k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
-                                                  C::K * C::P * C::N, gp);
+                                              C::K * C::P * C::N, gp);
   return (int)cudaGetLastError();
 }
 

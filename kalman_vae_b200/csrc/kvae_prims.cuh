@@ -91,17 +91,19 @@ template <int COLS> KV_FN void store_row(float* __restrict__ p, const float (&o)
 // Group of L lanes
 // ---------------------------------------------------------------------------------------
 template <int L, int R> struct Group {
-  int lane;  // lane within the group
+  int lane;       // lane within the group
+  unsigned mask;  // the warp lanes of this group: all group collectives name exactly these lanes, so groups
+                  // of one warp may diverge from each other (e.g. different time chunks) without deadlock
   KV_FN int row0() const { return L == 1 ? 0 : lane * R; }
   KV_FN void sync() const {
 #if defined(__CUDA_ARCH__)
-    if constexpr (L > 1) __syncwarp();
+    if constexpr (L > 1) __syncwarp(mask);
 #endif
   }
   // value held by lane `src` of this group
   KV_FN float bcast(float v, int src) const {
 #if defined(__CUDA_ARCH__)
-    if constexpr (L > 1) return __shfl_sync(0xffffffffu, v, src, L);
+    if constexpr (L > 1) return __shfl_sync(mask, v, src, L);
 #endif
     (void)src;
     return v;
@@ -111,7 +113,7 @@ template <int L, int R> struct Group {
 #if defined(__CUDA_ARCH__)
     if constexpr (L > 1) {
       KV_UNROLL for (int off = L / 2; off >= 1; off >>= 1) {
-        KV_UNROLL for (int i = 0; i < CNT; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+        KV_UNROLL for (int i = 0; i < CNT; ++i) v[i] += __shfl_xor_sync(mask, v[i], off);
       }
     }
 #endif

@@ -57,7 +57,7 @@ int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const k
 
 template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims& d) {
 #define X(l) \
-  if (d.lanes == (l)) { if constexpr (N % (l) == 0) return elbo_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B); }
+  if (d.lanes == (l)) { if constexpr (N % (l) == 0) return elbo_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B, d.T); }
   KV_FOR_EACH_L(X)
 #undef X
   return 0;

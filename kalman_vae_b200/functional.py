@@ -78,6 +78,18 @@ def prep(t, device=None):
 
 
 _info_cache = {}
+_ws_cache = {}
+
+
+def workspace(device, kind, nbytes):
+    """Persistent scratch per (device, stream, kind), grown on demand: kernels are stream-ordered, so the
+    same scratch can serve every call on that stream (no allocator traffic on the hot path)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, kind)
+    w = _ws_cache.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = w
+    return w
 
 
 def info_word(device):
@@ -127,7 +139,7 @@ def elbo_terms(pb: Problem, st: States, eps, jitter=1e-6, Y=None, U=None):
     """terms[8] (see include/kvae_kalman.h)."""
     dev = pb.Y.device
     terms = torch.empty(8, dtype=torch.float32, device=dev)
-    ws = torch.empty(max(capi.elbo_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
+    ws = workspace(dev, "elbo", capi.elbo_workspace_bytes(pb.dims))
     capi.elbo_fwd(pb.dims, pb.inputs(Y, U), st.c_struct(), eps, jitter, terms, ws, info_word(dev), dev)
     return terms
 
@@ -140,7 +152,7 @@ def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=N
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     grads = dict(dY=e(B, T, p), dU=e(B, T, m) if need_dU else None, dalpha=e(B, T, K),
                  dA=e(K, n, n), dBm=e(K, n, m), dC=e(K, p, n), dQ=e(K, n, n) if pb.q_per_mode else None)
-    ws = torch.empty(max(capi.bwd_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
+    ws = workspace(dev, "bwd", capi.bwd_workspace_bytes(pb.dims))
     capi.bwd(pb.dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
     return grads
 
@@ -155,7 +167,11 @@ class SmoothFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pb: Problem, smooth: bool, Y, U, alpha, A, Bm, C, Q):
         st, A_list, B_list, C_list = smooth_fwd(pb, smooth=smooth, lists=True)
-        ctx.pb, ctx.st, ctx.smooth = pb, st, smooth
+        ctx.pb, ctx.smooth = pb, smooth
+        # outputs are saved through save_for_backward: holding them on ctx directly would create a
+        # ctx -> output -> grad_fn -> ctx cycle that only the cyclic GC frees (device memory would pile up)
+        ctx.save_for_backward(*[t for t in (st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred,
+                                            st.mus_smooth, st.Sigmas_smooth) if t is not None])
         ctx.has_U = U is not None
         outs = [st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred, A_list, B_list]
         ctx.c_materialised = not pb.c_shared
@@ -167,7 +183,8 @@ class SmoothFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
-        pb, st = ctx.pb, ctx.st
+        pb = ctx.pb
+        st = States(*ctx.saved_tensors)
         gouts = list(gouts)
         names = (["mus_smooth", "Sigmas_smooth"] if ctx.smooth else []) + \
                 ["mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "A_list", "B_list"] + \

@@ -16,7 +16,7 @@ template <class C> static void run_fwd(const Args& a, const HostParams& hp, int 
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
   std::vector<float> tiles(FTiles<C>::warp_total + 4);
-  Group<C::L, C::R> g{0};
+  Group<C::L, C::R> g{0, 1u};
   FTiles<C> tl{tiles.data(), 0};
   for (int b = 0; b < a.B; ++b) {
     float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
@@ -53,10 +53,12 @@ template <class C> static void run_elbo(const Args& a, const HostParams& hp, flo
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
   std::vector<float> tiles(FTiles<C>::warp_total + 4);
-  Group<C::L, C::R> g{0};
+  Group<C::L, C::R> g{0, 1u};
   FTiles<C> tl{tiles.data(), 0};
   double acc[5] = {0, 0, 0, 0, 0};
-  for (int b = 0; b < a.B; ++b) elbo_sweep<C>(a, base.data(), tl, g, b, true, jitter, acc);
+  // cut every sequence into chunks of 3 steps to exercise the time-parallel chunk starts
+  for (int b = 0; b < a.B; ++b)
+    for (int t0 = 0; t0 < a.T; t0 += 3) elbo_sweep<C>(a, base.data(), tl, g, b, true, jitter, t0, t0 + 3 < a.T ? t0 + 3 : a.T, nullptr, acc);
   for (int i = 0; i < 5; ++i) acc5[i] = acc[i];
 }
 
@@ -90,7 +92,7 @@ template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParam
   const size_t nn = (size_t)a.B * a.T * C::N * C::N, nv = (size_t)a.B * a.T * C::N;
   std::vector<float> wSf(nn), wSp(nn), wmf(nv), wmp(nv);
   w.w_Sig_f = wSf.data(); w.w_Sig_p = wSp.data(); w.w_mu_f = wmf.data(); w.w_mu_p = wmp.data();
-  Group<C::L, C::R> g{0};
+  Group<C::L, C::R> g{0, 1u};
   for (int i = 0; i < GradAcc<C>::PSZ; ++i) gp[i] = 0.0;
   for (int b = 0; b < a.B; ++b) {
     GradAcc<C> acc;
