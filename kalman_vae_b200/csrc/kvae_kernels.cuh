@@ -3,11 +3,14 @@
 // memory; per-group publish tiles behind them.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
 #include "kvae_bwd.cuh"
 
 namespace kvae {
 
-constexpr int kThreads = 128;
+// threads per CTA: 4 warps; 2 warps for the large-state shapes (their per-warp tiles are big)
+template <class C> constexpr int TPB = (C::N >= 16) ? 64 : 128;
 
 struct BasePtrs { const float *A, *Bm, *C, *Q, *R, *mu0, *S0; };
 
@@ -25,7 +28,7 @@ template <class C> __device__ __forceinline__ Group<C::L, C::R> this_group() {
   return Group<C::L, C::R>{(int)(threadIdx.x % C::L), 0xffffffffu};
 }
 template <class C> constexpr size_t smem_bytes() {
-  return sizeof(float) * (size_t)(Base<C>::total + (kThreads / 32) * FTiles<C>::warp_total);
+  return sizeof(float) * (size_t)(Base<C>::total + (TPB<C> / 32) * FTiles<C>::warp_total);
 }
 // this thread's tile set: per-warp region + group index inside the warp
 template <class TS> __device__ __forceinline__ TS warp_tiles(float* tiles_all, int L) {
@@ -33,11 +36,11 @@ template <class TS> __device__ __forceinline__ TS warp_tiles(float* tiles_all, i
 }
 
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_filter_smooth(Args a, BasePtrs bp, int smooth) {
+__global__ void __launch_bounds__(TPB<C>) k_filter_smooth(Args a, BasePtrs bp, int smooth) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const int gi = threadIdx.x / C::L;
   const Group<C::L, C::R> g = this_group<C>();
   int b = blockIdx.x * GPB + gi;
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(kThreads) k_filter_smooth(Args a, BasePtrs bp,
 }
 
 template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth, cudaStream_t s) {
-  constexpr int GPB = kThreads / C::L;
+  (void)cudaGetLastError();  // do not inherit a stale (non-sticky) error from an earlier call
+  constexpr int GPB = TPB<C> / C::L;
   const size_t sm = smem_bytes<C>();
   static bool attr_set = false;  // benign race: idempotent
   if (sm > 48 * 1024 && !attr_set) {
@@ -59,8 +63,11 @@ template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth,
     attr_set = true;
   }
   const int grid = (a.B + GPB - 1) / GPB;
-  k_filter_smooth<C><<<grid, kThreads, sm, s>>>(a, bp, smooth);
-  return (int)cudaGetLastError();
+  constexpr int tpb = TPB<C>;
+  k_filter_smooth<C><<<grid, tpb, sm, s>>>(a, bp, smooth);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess && getenv("KVAE_DEBUG")) fprintf(stderr, "[kvae] k_filter_smooth launch failed: smem=%zu grid=%d L=%d: %s\n", sm, grid, C::L, cudaGetErrorString(e));
+  return (int)e;
 }
 
 
@@ -92,7 +99,7 @@ inline ChunkMap make_chunks(int B, int T, int L) {
 // sequences, so control flow stays warp-uniform; inactive tail groups mirror the last sequence, store nothing
 template <class C>
 __device__ __forceinline__ bool chunk_of(const Args& a, ChunkMap cm, int& b, int& t0, int& t1) {
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const int c = blockIdx.x % cm.chunks;
   b = (blockIdx.x / cm.chunks) * GPB + threadIdx.x / C::L;
   const bool active = b < a.B;
@@ -102,7 +109,7 @@ __device__ __forceinline__ bool chunk_of(const Args& a, ChunkMap cm, int& b, int
   return active && t0 < a.T;
 }
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float jitter, ChunkMap cm, double* __restrict__ partials) {
+__global__ void __launch_bounds__(TPB<C>) k_elbo(Args a, BasePtrs bp, float jitter, ChunkMap cm, double* __restrict__ partials) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float ji
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   elbo_sweep<C>(a, base, tl, g, b, active, jitter, t0, t1, nullptr, acc);
   // block reduction (fixed order -> deterministic)
-  __shared__ double red[kThreads / 32][5];
+  __shared__ double red[TPB<C> / 32][5];
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     double v = acc[i];
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) k_elbo(Args a, BasePtrs bp, float ji
   if (threadIdx.x < 5) {
     double v = 0.0;
 #pragma unroll
-    for (int wq = 0; wq < kThreads / 32; ++wq) v += red[wq][threadIdx.x];
+    for (int wq = 0; wq < TPB<C> / 32; ++wq) v += red[wq][threadIdx.x];
     partials[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
   }
 }
@@ -153,7 +160,7 @@ static __global__ void k_elbo_final(const double* __restrict__ partials, int nbl
 }
 
 template <class C> int chunk_grid(int B, int chunks) {
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   return ((B + GPB - 1) / GPB) * chunks;
 }
 template <class C> size_t elbo_ws_bytes(int B, int T) {
@@ -161,7 +168,7 @@ template <class C> size_t elbo_ws_bytes(int B, int T) {
 }
 
 template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitter, float* terms, void* ws, cudaStream_t s) {
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const size_t sm = smem_bytes_elbo<C>();
   static bool attr_set = false;
   if (sm > 48 * 1024 && !attr_set) {
@@ -171,7 +178,8 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
   }
   const ChunkMap cm = make_chunks(a.B, a.T, C::L);
   const int grid = chunk_grid<C>(a.B, cm.chunks);
-  k_elbo<C><<<grid, kThreads, sm, s>>>(a, bp, jitter, cm, reinterpret_cast<double*>(ws));
+  constexpr int tpb = TPB<C>;
+  k_elbo<C><<<grid, tpb, sm, s>>>(a, bp, jitter, cm, reinterpret_cast<double*>(ws));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   k_elbo_final<<<1, 160, 0, s>>>(reinterpret_cast<const double*>(ws), grid, terms);
@@ -185,7 +193,7 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
 struct GradPtrs { float *dA, *dB, *dC, *dQ; };
 
 template <class C> constexpr size_t smem_floats_bwd() {
-  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(kThreads / 32) * BTiles<C>::warp_total;
+  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(TPB<C> / 32) * BTiles<C>::warp_total;
   constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
   return tiles > red ? tiles : red;
 }
@@ -202,23 +210,23 @@ __device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L
     for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
   }
   __syncthreads();   // tiles are dead: reuse them
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) red[i] = 0.f;
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int wq = 0; wq < kThreads / 32; ++wq) {
+  for (int wq = 0; wq < TPB<C> / 32; ++wq) {
     if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += kThreads) partial_row[i] = red[i];
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
 }
 
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
+__global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
                                                   const float* __restrict__ terms, float* __restrict__ partials) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const int gi = threadIdx.x / C::L;
   const Group<C::L, C::R> g = this_group<C>();
   int b = blockIdx.x * GPB + gi;
@@ -255,7 +263,7 @@ static __global__ void k_param_final(const float* __restrict__ partials, int nbl
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <class C> size_t bwd_ws_bytes(int B, int T) {
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const size_t nn = align256(sizeof(float) * (size_t)B * T * C::N * C::N);
   const size_t nv = align256(sizeof(float) * (size_t)B * T * C::N);
   const size_t rows = (size_t)((B + GPB - 1) / GPB);
@@ -265,7 +273,7 @@ template <class C> size_t bwd_ws_bytes(int B, int T) {
 template <class C>
 int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo, const float* terms, void* ws,
                GradPtrs gp, cudaStream_t s) {
-  constexpr int GPB = kThreads / C::L;
+  constexpr int GPB = TPB<C> / C::L;
   const size_t sm = sizeof(float) * smem_floats_bwd<C>();
   static bool attr_set = false;
   if (sm > 48 * 1024 && !attr_set) {
@@ -283,7 +291,8 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   float* partials = reinterpret_cast<float*>(p);
   constexpr int psz = GradAcc<C>::PSZ;
   const int grid = (a.B + GPB - 1) / GPB;
-  k_bwd<C><<<grid, kThreads, sm, s>>>(a, w, bp, g_elbo, terms, partials);
+  constexpr int tpb = TPB<C>;
+  k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
