@@ -62,62 +62,87 @@ template <int R> KV_FN void load_vec_opt(const float* p, long off, float (&dst)[
 // Parameter-gradient accumulators held in registers (A.0 adjoint):
 //   dA_k += alpha_k Abar_t ... ; returns the partial <Abar_t, A_k> + ... for dalpha.
 // ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define KV_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+#define KV_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
+
 template <class C> struct GradAcc {
   static constexpr int K = C::K, R = C::R, N = C::N, M = C::M, P = C::P;
   static constexpr int KQ = C::QPM ? C::K : 0;
   static constexpr int oA = 0, oB = oA + K * R * N, oCt = oB + K * R * M, oQ = oCt + C::KC * R * P;
   static constexpr int count = oQ + KQ * R * N;
-  float v[count];
   // flat parameter layout of the reduced gradient: dA [K][N][N] | dB [K][N][M] | dC [K][P][N] | dQ [K][N][N]
-  static constexpr int PSZ = K * N * N + K * N * M + K * P * N + KQ * N * N;
+  static constexpr int fA = 0, fB = K * N * N, fC = fB + K * N * M, fQ = fC + K * P * N;
+  static constexpr int PSZ = fQ + KQ * N * N;
+  // One register accumulator per (mode,row,col) element of the lane's rows.  For n = 16 that is 392 floats
+  // per lane and spills to local memory; the alternative kept below (SM: a per-CTA shared-memory accumulator
+  // updated with atomics) was measured 2.2x SLOWER on B200 (cfg4/8: 73.8 ms vs 32.8 ms), so it is off.
+  // The planned fix is a dense per-step store + a separate mode-contraction kernel.
+  static constexpr bool SM = false;
+  float v[SM ? 1 : count];
+  float* sacc;  // SM mode: [PSZ] floats in shared memory, zeroed by the kernel
+  bool on;      // SM mode: false for tail groups that mirror a valid sequence (they must not contribute)
 
   KV_FN void zero() {
-    KV_UNROLL for (int i = 0; i < count; ++i) v[i] = 0.f;
+    KV_UNROLL for (int i = 0; i < (SM ? 1 : count); ++i) v[i] = 0.f;
   }
   // dal[k] += <Xbar, X_k> over own rows (caller all-reduces); acc_k += al[k] * Xbar
-  template <int COLS, int OFF>
+  // OFF: register offset of the block, FOFF: flat offset, TR: block is stored transposed in the flat layout (C^T)
+  template <int COLS, int OFF, int FOFF, bool TR, int MODES>
   KV_FN void one(const float* basek, int row0, const float (&al)[K], const float (&Xb)[R][COLS], float (&dal)[K]) {
-    KV_UNROLL for (int k = 0; k < K; ++k) {
+    KV_UNROLL for (int k = 0; k < MODES; ++k) {
       float s = 0.f;
       KV_UNROLL for (int r = 0; r < R; ++r) {
         float row[COLS];
         load_row<COLS>(basek + (k * N + row0 + r) * COLS, row);
         KV_UNROLL for (int j = 0; j < COLS; ++j) {
           s = fmaf(Xb[r][j], row[j], s);
-          v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
+          if constexpr (SM) {
+            const int flat = TR ? FOFF + (k * COLS + j) * N + row0 + r : FOFF + (k * N + row0 + r) * COLS + j;
+            if (on) KV_ATOMIC_ADD(sacc + flat, al[k] * Xb[r][j]);
+          } else {
+            v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
+          }
         }
       }
       dal[k] += s;
     }
   }
   KV_FN void addA(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K]) {
-    one<N, oA>(base + Base<C>::oA, row0, al, Xb, dal);
+    one<N, oA, fA, false, K>(base + Base<C>::oA, row0, al, Xb, dal);
   }
   KV_FN void addB(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][M], float (&dal)[K]) {
-    one<M, oB>(base + Base<C>::oB, row0, al, Xb, dal);
+    one<M, oB, fB, false, K>(base + Base<C>::oB, row0, al, Xb, dal);
   }
   KV_FN void addQ(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K]) {
-    if constexpr (C::QPM) one<N, oQ>(base + Base<C>::oQ, row0, al, Xb, dal);
+    if constexpr (C::QPM) one<N, oQ, fQ, false, K>(base + Base<C>::oQ, row0, al, Xb, dal);
   }
   KV_FN void addCt(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][P], float (&dal)[K]) {
     if constexpr (C::CSH) {
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) v[oCt + r * P + j] += Xb[r][j];
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) {
+        if constexpr (SM) { if (on) KV_ATOMIC_ADD(sacc + fC + j * N + row0 + r, Xb[r][j]); }
+        else v[oCt + r * P + j] += Xb[r][j];
+      }
     } else {
-      one<P, oCt>(base + Base<C>::oCt, row0, al, Xb, dal);
+      one<P, oCt, fC, true, K>(base + Base<C>::oCt, row0, al, Xb, dal);
     }
   }
-  // f(flat parameter index, value) for every accumulator element of the lane owning rows row0..
+  // f(flat parameter index, value) for every register accumulator of the lane owning rows row0.. (register mode)
   template <class F> KV_FN void for_each(int row0, F&& f) const {
-    KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
-      f((k * N + row0 + r) * N + j, v[oA + (k * R + r) * N + j]);
-    KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < M; ++j)
-      f(K * N * N + (k * N + row0 + r) * M + j, v[oB + (k * R + r) * M + j]);
-    KV_UNROLL for (int k = 0; k < C::KC; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j)
-      f(K * N * N + K * N * M + (k * P + j) * N + row0 + r, v[oCt + (k * R + r) * P + j]);
-    if constexpr (C::QPM) {
+    if constexpr (!SM) {
       KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
-        f(K * N * N + K * N * M + K * P * N + (k * N + row0 + r) * N + j, v[oQ + (k * R + r) * N + j]);
-    }
+        f(fA + (k * N + row0 + r) * N + j, v[oA + (k * R + r) * N + j]);
+      KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < M; ++j)
+        f(fB + (k * N + row0 + r) * M + j, v[oB + (k * R + r) * M + j]);
+      KV_UNROLL for (int k = 0; k < C::KC; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j)
+        f(fC + (k * P + j) * N + row0 + r, v[oCt + (k * R + r) * P + j]);
+      if constexpr (C::QPM) {
+        KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
+          f(fQ + (k * N + row0 + r) * N + j, v[oQ + (k * R + r) * N + j]);
+      }
+    } else { (void)row0; (void)f; }
   }
 };
 

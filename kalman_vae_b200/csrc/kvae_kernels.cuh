@@ -194,6 +194,7 @@ struct GradPtrs { float *dA, *dB, *dC, *dQ; };
 
 template <class C> constexpr size_t smem_floats_bwd() {
   constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(TPB<C> / 32) * BTiles<C>::warp_total;
+  if (GradAcc<C>::SM) return tiles + (size_t)GradAcc<C>::PSZ;   // accumulator lives beside the tiles
   constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
   return tiles > red ? tiles : red;
 }
@@ -203,21 +204,27 @@ template <class C> constexpr size_t smem_floats_bwd() {
 template <class C>
 __device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L, C::R>& g, bool active, float* red,
                                                float* __restrict__ partial_row) {
-  if (!active) acc.zero();
-#pragma unroll
-  for (int off = C::L; off < 32; off <<= 1) {
-#pragma unroll
-    for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
-  }
-  __syncthreads();   // tiles are dead: reuse them
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int wq = 0; wq < TPB<C> / 32; ++wq) {
-    if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
+  if constexpr (GradAcc<C>::SM) {   // already accumulated per CTA in shared memory (inactive groups added nothing)
+    (void)g; (void)active; (void)red;
     __syncthreads();
+    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = acc.sacc[i];
+  } else {
+    if (!active) acc.zero();
+#pragma unroll
+    for (int off = C::L; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
+    }
+    __syncthreads();   // tiles are dead: reuse them
+    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int wq = 0; wq < TPB<C> / 32; ++wq) {
+      if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
   }
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
 }
 
 template <class C>
@@ -236,6 +243,13 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   w.c_elbo = g_elbo ? (*g_elbo) * terms[6] : 0.f;
   GradAcc<C> acc;
   acc.zero();
+  acc.sacc = nullptr;
+  acc.on = active;
+  if constexpr (GradAcc<C>::SM) {
+    acc.sacc = tiles_all + (TPB<C> / 32) * BTiles<C>::warp_total;
+    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) acc.sacc[i] = 0.f;
+    __syncthreads();
+  }
   bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
   bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
   cta_reduce_acc<C>(acc, g, active, tiles_all, partials + (size_t)blockIdx.x * GradAcc<C>::PSZ);

@@ -97,9 +97,13 @@ template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParam
   for (int b = 0; b < a.B; ++b) {
     GradAcc<C> acc;
     acc.zero();
+    std::vector<float> sacc(GradAcc<C>::PSZ, 0.f);
+    acc.sacc = sacc.data();
+    acc.on = true;
     bwd_sweep3<C>(a, w, base.data(), tl, g, b, true, acc);
     bwd_sweep4<C>(a, w, base.data(), tl, g, b, true, acc);
-    acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
+    if (GradAcc<C>::SM) { for (int i = 0; i < GradAcc<C>::PSZ; ++i) gp[i] += (double)sacc[i]; }
+    else acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
   }
   if (dbg) {
     memcpy(dbg[0], wSf.data(), nn * 4); memcpy(dbg[1], wSp.data(), nn * 4);
