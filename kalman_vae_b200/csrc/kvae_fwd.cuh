@@ -87,6 +87,67 @@ template <class C> KV_FN void load_step(const Args& a, long bt, StepIn<C>& s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Input staging: the per-step inputs of a sequence (y_t, u_t, alpha_t, mask_t: 4*(P+M+K+1) bytes) are
+// tiny, so fetching them step by step costs one L1 wavefront per stream per group per step.  Instead a
+// group fetches FOUR time steps at once with 128-bit loads (one 16-byte piece per lane and load), keeps
+// the chunk pending in registers while it works on the previous one, then drops it into a per-group
+// shared-memory slot from which every lane reads its step with broadcast loads.
+// Needs T % 4 == 0 (all pieces 16-byte aligned); otherwise the callers use load_step().
+// ---------------------------------------------------------------------------------------
+template <class C, bool WITH_YUM> struct InStage {
+  static constexpr int P = C::P, M = C::M, K = C::K, L = C::L;
+  static constexpr int oY = 0, oU = 4 * P, oA = oU + 4 * M, oM = oA + 4 * K;
+  static constexpr int chunk_floats = oM + 4;
+  static constexpr int NPIECE = WITH_YUM ? (P + M + K + 1) : K;   // 16-byte pieces per 4-step chunk
+  static constexpr int PER_LANE = (NPIECE + L - 1) / L;
+  // per-group slot, padded so that the groups of a warp start 4 banks apart
+  static constexpr int group_floats = pad_res(chunk_floats, L == 1 ? 4 : (L < 32 ? 4 : L));
+  f4 pend[PER_LANE];
+  float* slot;
+
+  // piece q of the chunk starting at step index bt0 (= b*T + t0, t0 % 4 == 0)
+  KV_FN f4 fetch(const Args& a, long bt0, int q) const {
+    const float* src = nullptr;
+    if (WITH_YUM) {
+      if (q < P) src = a.Y + bt0 * P + 4 * q;
+      else if (q < P + M) src = a.U ? a.U + bt0 * M + 4 * (q - P) : nullptr;
+      else if (q < P + M + K) src = a.alpha + bt0 * K + 4 * (q - P - M);
+      else src = a.mask ? a.mask + bt0 + 0 : nullptr;
+      if (src == nullptr) { const float v = (q < P + M) ? 0.f : 1.f; return f4{v, v, v, v}; }
+    } else {
+      src = a.alpha + bt0 * K + 4 * q;
+    }
+    return *reinterpret_cast<const f4*>(src);
+  }
+  KV_FN int slot_off(int q) const {
+    if (WITH_YUM) return 4 * q;            // Y pieces, U pieces, alpha pieces, mask piece are laid out back to back
+    return oA + 4 * q;
+  }
+  KV_FN void prefetch(const Args& a, const Group<C::L, C::R>& g, long bt0) {
+    KV_UNROLL for (int i = 0; i < PER_LANE; ++i) {
+      const int q = g.lane + i * L;
+      if (q < NPIECE) pend[i] = fetch(a, bt0, q);
+    }
+  }
+  KV_FN void commit(const Group<C::L, C::R>& g) {
+    g.sync();
+    KV_UNROLL for (int i = 0; i < PER_LANE; ++i) {
+      const int q = g.lane + i * L;
+      if (q < NPIECE) *reinterpret_cast<f4*>(slot + slot_off(q)) = pend[i];
+    }
+    g.sync();
+  }
+  KV_FN void read(int s, StepIn<C>& in) const {   // s = step within the chunk (0..3)
+    if (WITH_YUM) {
+      KV_UNROLL for (int j = 0; j < P; ++j) in.y[j] = slot[oY + s * P + j];
+      KV_UNROLL for (int j = 0; j < M; ++j) in.u[j] = slot[oU + s * M + j];
+      in.m = slot[oM + s];
+    }
+    KV_UNROLL for (int k = 0; k < K; ++k) in.al[k] = slot[oA + s * K + k];
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // A.0  mixing: own rows of A_t, B_t, C_t^T, Q_t
 // ---------------------------------------------------------------------------------------
 template <class C, int COLS>
@@ -170,7 +231,7 @@ KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)
 // ---------------------------------------------------------------------------------------
 template <class C>
 KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
-                        float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R]) {
+                        float* stage_slot, float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
   const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), CB = tl.np(0), KB = tl.np(1), VB = tl.vec(0);
@@ -185,10 +246,20 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
   else load_row<N>(base + Base<C>::oMu0, mu);
 
   StepIn<C> cur, nxt;
-  load_step<C>(a, (long)b * T, cur);
+  const bool staged = (T % 4 == 0);
+  InStage<C, true> ins;
+  ins.slot = stage_slot;
+  if (staged) {
+    ins.prefetch(a, g, (long)b * T);
+    ins.commit(g);
+    if (T > 4) ins.prefetch(a, g, (long)b * T + 4);
+  } else {
+    load_step<C>(a, (long)b * T, cur);
+  }
   for (int t = 0; t < T; ++t) {
     const long bt = (long)b * T + t;
-    if (t + 1 < T) load_step<C>(a, bt + 1, nxt);  // software prefetch of the next step's inputs
+    if (staged) ins.read(t & 3, cur);
+    else if (t + 1 < T) load_step<C>(a, bt + 1, nxt);  // software prefetch of the next step's inputs
 
     float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
     mix_A<C>(base, cur.al, row0, A);
@@ -279,7 +350,14 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = Sf[r][j];
     allgather<MEM, L, R>(g, muf, VB, mu);
     KV_UNROLL for (int r = 0; r < R; ++r) mu_own[r] = muf[r];
-    cur = nxt;
+    if (staged) {
+      if ((t & 3) == 3 && t + 1 < T) {      // next chunk: publish the pending one, start fetching the one after
+        ins.commit(g);
+        if (t + 5 < T) ins.prefetch(a, g, bt + 5);
+      }
+    } else {
+      cur = nxt;
+    }
   }
   if (!ok && active) *a.info = 1;
 }
@@ -309,7 +387,7 @@ KV_FN bool smoother_gain(const Group<C::L, C::R>& g, TileRef XA, TileRef XL, con
 // ---------------------------------------------------------------------------------------
 template <class C>
 KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
-                          float (&Sig)[C::R][C::N], float (&mus)[C::R]) {
+                          float* stage_slot, float (&Sig)[C::R][C::N], float (&mus)[C::R]) {
   constexpr int N = C::N, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
   const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), VB = tl.vec(0);
@@ -323,10 +401,28 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       store_row<R>(a.mu_s + bt * N + row0, mus);
     }
   }
+  const bool staged = (T % 4 == 0) && T >= 4;
+  InStage<C, false> ins;
+  ins.slot = stage_slot;
+  if (staged) {   // chunk holding alpha_{T-1}, then keep one chunk ahead (towards t = 0)
+    ins.prefetch(a, g, (long)b * T + (T - 4));
+    ins.commit(g);
+    if (T >= 8) ins.prefetch(a, g, (long)b * T + (T - 8));
+  }
   for (int t = T - 2; t >= 0; --t) {
     const long bt = (long)b * T + t;
     float al1[C::K];
-    load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
+    if (staged) {
+      StepIn<C> tmp;
+      ins.read((t + 1) & 3, tmp);
+      KV_UNROLL for (int k = 0; k < C::K; ++k) al1[k] = tmp.al[k];
+      if (((t + 1) & 3) == 0 && t >= 0 && t + 1 >= 4) {   // alpha_{t+1} was the first step of its chunk: switch to the previous chunk
+        ins.commit(g);
+        if (t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
+      }
+    } else {
+      load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
+    }
     float Sf[R][N], Sp1[R][N], muf[R], mup1[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
       load_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);

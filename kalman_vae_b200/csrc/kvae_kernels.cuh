@@ -28,7 +28,8 @@ template <class C> __device__ __forceinline__ Group<C::L, C::R> this_group() {
   return Group<C::L, C::R>{(int)(threadIdx.x % C::L), 0xffffffffu};
 }
 template <class C> constexpr size_t smem_bytes() {
-  return sizeof(float) * (size_t)(Base<C>::total + (TPB<C> / 32) * FTiles<C>::warp_total);
+  return sizeof(float) * (size_t)(Base<C>::total + (TPB<C> / 32) * FTiles<C>::warp_total +
+                                  (TPB<C> / C::L) * InStage<C, true>::group_floats);
 }
 // this thread's tile set: per-warp region + group index inside the warp
 template <class TS> __device__ __forceinline__ TS warp_tiles(float* tiles_all, int L) {
@@ -47,9 +48,10 @@ __global__ void __launch_bounds__(TPB<C>) k_filter_smooth(Args a, BasePtrs bp, i
   const bool active = b < a.B;
   if (!active) b = a.B - 1;  // tail groups recompute the last sequence and store nothing
   const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
+  float* stage_slot = tiles_all + (TPB<C> / 32) * FTiles<C>::warp_total + gi * InStage<C, true>::group_floats;
   float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
-  filter_sweep<C>(a, base, tl, g, b, active, Sig, mu, mu_own);
-  if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, Sig, mu_own);
+  filter_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own);
+  if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu_own);
 }
 
 template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth, cudaStream_t s) {

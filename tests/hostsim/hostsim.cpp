@@ -20,8 +20,9 @@ template <class C> static void run_fwd(const Args& a, const HostParams& hp, int 
   FTiles<C> tl{tiles.data(), 0};
   for (int b = 0; b < a.B; ++b) {
     float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
-    filter_sweep<C>(a, base.data(), tl, g, b, true, Sig, mu, mu_own);
-    if (smooth) smoother_sweep<C>(a, base.data(), tl, g, b, true, Sig, mu_own);
+    alignas(16) float slot[InStage<C, true>::group_floats + 4];
+    filter_sweep<C>(a, base.data(), tl, g, b, true, slot, Sig, mu, mu_own);
+    if (smooth) smoother_sweep<C>(a, base.data(), tl, g, b, true, slot, Sig, mu_own);
   }
 }
 
