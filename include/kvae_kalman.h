@@ -39,7 +39,8 @@
 extern "C" {
 #endif
 
-#define KVAE_ABI_VERSION 1
+#define KVAE_ABI_VERSION 2
+#define KVAE_FLAG_SMOOTH_ONLY 1  /* kvae_dims.flags: forward entry skips the filter sweep (states given) */
 
 typedef struct kvae_dims {
   int32_t B;          /* sequences in this call (the per-rank shard)               */
@@ -52,6 +53,7 @@ typedef struct kvae_dims {
                       /* 0: Q is [n,n] fixed (lstm, KalmanFilter.Q buffer)        */
   int32_t c_shared;   /* 1: C_t = C[0] (switching); 0: C_t = sum_k alpha_k C_k    */
   int32_t lanes;      /* lanes of a warp that own one sequence; 0 = library picks */
+  int32_t flags;      /* KVAE_FLAG_* (forward entry only)                         */
 } kvae_dims;
 
 /* problem inputs shared by all entry points */
@@ -69,6 +71,14 @@ typedef struct kvae_inputs {
   const float* Sigma0; /* [n,n]                                                     */
   const float* mu_init;    /* [B,n]   optional per-sequence initial belief (NULL = mu0)     */
   const float* Sigma_init; /* [B,n,n] optional per-sequence initial belief (NULL = Sigma0)  */
+  /* Explicit per-step matrices for the FORWARD entry (all NULL = mix from alpha).  With A_dense given
+   * the kernel reads A_t,B_t,C_t (and Q_t if Q_dense) from these [B,T,...] tensors and ignores alpha
+   * (which may be NULL): the per-step forms KalmanFilter.filter_step kalman_filter.py:31-104 and
+   * .smooth_step :204-237 are T=1 / T=2 calls of this kind. */
+  const float* A_dense;    /* [B,T,n,n] */
+  const float* B_dense;    /* [B,T,n,m] */
+  const float* C_dense;    /* [B,T,p,n] */
+  const float* Q_dense;    /* [B,T,n,n] or NULL */
 } kvae_inputs;
 
 /* the six state tensors (written by the forward pass, read by ELBO / backward) */

@@ -16,12 +16,12 @@ LIB_PATH = os.path.join(_HERE, "libkvae_kalman.so")
 
 
 class KvaeDims(Structure):
-    _fields_ = [(k, c_int32) for k in ("B", "T", "n", "p", "m", "K", "q_per_mode", "c_shared", "lanes")]
+    _fields_ = [(k, c_int32) for k in ("B", "T", "n", "p", "m", "K", "q_per_mode", "c_shared", "lanes", "flags")]
 
 
 class KvaeInputs(Structure):
     _fields_ = [(k, c_void_p) for k in ("Y", "U", "mask", "alpha", "A", "Bm", "C", "Q", "R", "mu0", "Sigma0",
-                                        "mu_init", "Sigma_init")]
+                                        "mu_init", "Sigma_init", "A_dense", "B_dense", "C_dense", "Q_dense")]
 
 
 class KvaeStates(Structure):
@@ -70,7 +70,7 @@ def lib():
     L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
                               c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads), c_void_p,
                               c_void_p, c_int, c_void_p]
-    if L.kvae_abi_version() != 1:
+    if L.kvae_abi_version() != 2:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
     return L
@@ -104,8 +104,11 @@ def _check(rc, what):
         raise KvaeError(f"{what} failed (status {rc}): {lib().kvae_last_error().decode()}")
 
 
-def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0):
-    return KvaeDims(B, T, n, p, m, K, int(bool(q_per_mode)), int(bool(c_shared)), int(lanes))
+FLAG_SMOOTH_ONLY = 1
+
+
+def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0, flags=0):
+    return KvaeDims(B, T, n, p, m, K, int(bool(q_per_mode)), int(bool(c_shared)), int(lanes), int(flags))
 
 
 def supported(dims) -> bool:
@@ -116,10 +119,12 @@ def pick_lanes(dims) -> int:
     return int(lib().kvae_pick_lanes(byref(dims)))
 
 
-def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Sigma_init=None):
+def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Sigma_init=None,
+                A_dense=None, B_dense=None, C_dense=None, Q_dense=None):
     dev = Y.device
-    names = ("Y", "U", "mask", "alpha", "A", "Bm", "C", "Q", "R", "mu0", "Sigma0", "mu_init", "Sigma_init")
-    vals = (Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init, Sigma_init)
+    names = ("Y", "U", "mask", "alpha", "A", "Bm", "C", "Q", "R", "mu0", "Sigma0", "mu_init", "Sigma_init",
+             "A_dense", "B_dense", "C_dense", "Q_dense")
+    vals = (Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init, Sigma_init, A_dense, B_dense, C_dense, Q_dense)
     return KvaeInputs(*[_ptr(v, k, dev) for k, v in zip(names, vals)])
 
 

@@ -57,8 +57,10 @@ static int check_common(const kvae_dims* d, const kvae_inputs* in, const kvae_st
   *dd = *d;
   if (dd->lanes == 0) dd->lanes = pick_lanes(*dd);
   if (!kvae_supported(dd)) return fail(-2, "unsupported (n,p,m,K,lanes): see kvae_configs.h");
-  if (!in->Y || !in->alpha || !in->A || !in->Bm || !in->C || !in->Q || !in->R || !in->mu0 || !in->Sigma0)
+  if (!in->Y || !in->A || !in->Bm || !in->C || !in->Q || !in->R || !in->mu0 || !in->Sigma0)
     return fail(-1, "null input tensor");
+  if (!in->alpha && !in->A_dense) return fail(-1, "alpha is null and no explicit A_dense/B_dense/C_dense given");
+  if (in->A_dense && (!in->B_dense || !in->C_dense)) return fail(-1, "A_dense needs B_dense and C_dense");
   if (!st->mus_filt || !st->Sigmas_filt || !st->mus_pred || !st->Sigmas_pred) return fail(-1, "null state tensor");
   return 0;
 }
@@ -69,6 +71,7 @@ int kvae_kf_filter_smooth_fwd(const kvae_dims* d, const kvae_inputs* in, const k
   if (int rc = check_common(d, in, st, &dd)) return rc;
   if (!info) return fail(-1, "info must not be null");
   if ((st->mus_smooth == nullptr) != (st->Sigmas_smooth == nullptr)) return fail(-1, "mus_smooth/Sigmas_smooth: both or neither");
+  if ((dd.flags & KVAE_FLAG_SMOOTH_ONLY) && !st->mus_smooth) return fail(-1, "smooth-only call without smoothed-state buffers");
   DeviceGuard guard(device);
 #define X(n_, p_, m_, k_)                                                                                   \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
@@ -99,6 +102,7 @@ int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_state
   if (int rc = check_common(d, in, st, &dd)) return rc;
   if (!info || !eps || !terms || !workspace) return fail(-1, "null argument");
   if (!st->mus_smooth || !st->Sigmas_smooth) return fail(-1, "smoothed states required");
+  if (in->A_dense) return fail(-2, "explicit per-step matrices are supported by the forward entry only");
   DeviceGuard guard(device);
 #define X(n_, p_, m_, k_)                                                                                   \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
@@ -133,6 +137,7 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
   if (g_elbo && (!eps || !terms)) return fail(-1, "g_elbo given without eps/terms");
   if (!grads->dY || !grads->dalpha || !grads->dA || !grads->dBm || !grads->dC) return fail(-1, "null gradient buffer");
   if (dd.q_per_mode && !grads->dQ) return fail(-1, "dQ required when q_per_mode");
+  if (in->A_dense) return fail(-2, "explicit per-step matrices are supported by the forward entry only");
   DeviceGuard guard(device);
   kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace};
 #define X(n_, p_, m_, k_)                                                                                   \

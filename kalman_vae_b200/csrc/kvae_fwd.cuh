@@ -28,6 +28,14 @@ struct Args {
   // optional initial belief per sequence (single-step / chunked filtering); nullable -> mu0/Sigma0
   const float* mu_init;   // [B,N]
   const float* Sig_init;  // [B,N,N]
+  // optional explicit per-step matrices (forward kernels only): when dA is given the kernels read
+  // A_t,B_t,C_t(,Q_t) from these instead of mixing the base matrices (filter_step / smooth_step forms,
+  // kalman_filter.py:31,204).  Same layouts as A_list/B_list/C_list.
+  const float* dA;   // [B,T,N,N]
+  const float* dB;   // [B,T,N,M]
+  const float* dC;   // [B,T,P,N]
+  const float* dQ;   // [B,T,N,N]  nullable -> base Q
+  int smooth_only;   // 1: skip the filter sweep, smooth from the filtered states already in mu_f / Sig_f
   int* info;  // device word, set to nonzero if a Cholesky pivot was not positive
 };
 
@@ -82,7 +90,8 @@ template <class C> KV_FN void load_step(const Args& a, long bt, StepIn<C>& s) {
   load_row<C::P>(a.Y + bt * C::P, s.y);
   if (a.U) load_row<C::M>(a.U + bt * C::M, s.u);
   else { KV_UNROLL for (int j = 0; j < C::M; ++j) s.u[j] = 0.f; }
-  load_row<C::K>(a.alpha + bt * C::K, s.al);
+  if (a.alpha) load_row<C::K>(a.alpha + bt * C::K, s.al);
+  else { KV_UNROLL for (int k = 0; k < C::K; ++k) s.al[k] = 0.f; }
   s.m = a.mask ? a.mask[bt] : 1.0f;
 }
 
@@ -111,10 +120,11 @@ template <class C, bool WITH_YUM> struct InStage {
     if (WITH_YUM) {
       if (q < P) src = a.Y + bt0 * P + 4 * q;
       else if (q < P + M) src = a.U ? a.U + bt0 * M + 4 * (q - P) : nullptr;
-      else if (q < P + M + K) src = a.alpha + bt0 * K + 4 * (q - P - M);
+      else if (q < P + M + K) { if (a.alpha == nullptr) return f4{0.f, 0.f, 0.f, 0.f}; src = a.alpha + bt0 * K + 4 * (q - P - M); }
       else src = a.mask ? a.mask + bt0 + 0 : nullptr;
       if (src == nullptr) { const float v = (q < P + M) ? 0.f : 1.f; return f4{v, v, v, v}; }
     } else {
+      if (a.alpha == nullptr) return f4{0.f, 0.f, 0.f, 0.f};
       src = a.alpha + bt0 * K + 4 * q;
     }
     return *reinterpret_cast<const f4*>(src);
@@ -180,6 +190,24 @@ template <class C> KV_FN void mix_Ct(const float* base, const float (&al)[C::K],
 template <class C> KV_FN void mix_Q(const float* base, const float (&al)[C::K], int row0, float (&Q)[C::R][C::N]) {
   if constexpr (C::QPM) mix_one<C, C::N>(base + Base<C>::oQ, C::K, al, row0, Q);
   else copy_rows<C, C::N>(base + Base<C>::oQ, row0, Q);
+}
+
+// explicit-matrix variants (forward kernels): read the step's rows from dense per-step tensors when given
+template <class C> KV_FN void get_A(const Args& a, const float* base, const float (&al)[C::K], int row0, long bt, float (&A)[C::R][C::N]) {
+  if (a.dA) { KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<C::N>(a.dA + (bt * C::N + row0 + r) * C::N, A[r]); }
+  else mix_A<C>(base, al, row0, A);
+}
+template <class C> KV_FN void get_B(const Args& a, const float* base, const float (&al)[C::K], int row0, long bt, float (&Bm)[C::R][C::M]) {
+  if (a.dA) { KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<C::M>(a.dB + (bt * C::N + row0 + r) * C::M, Bm[r]); }
+  else mix_B<C>(base, al, row0, Bm);
+}
+template <class C> KV_FN void get_Ct(const Args& a, const float* base, const float (&al)[C::K], int row0, long bt, float (&Ct)[C::R][C::P]) {
+  if (a.dA) { KV_UNROLL for (int r = 0; r < C::R; ++r) KV_UNROLL for (int q = 0; q < C::P; ++q) Ct[r][q] = a.dC[(bt * C::P + q) * C::N + row0 + r]; }
+  else mix_Ct<C>(base, al, row0, Ct);
+}
+template <class C> KV_FN void get_Q(const Args& a, const float* base, const float (&al)[C::K], int row0, long bt, float (&Q)[C::R][C::N]) {
+  if (a.dA && a.dQ) { KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<C::N>(a.dQ + (bt * C::N + row0 + r) * C::N, Q[r]); }
+  else mix_Q<C>(base, al, row0, Q);
 }
 
 // Everything a filter step recomputes that the adjoint also needs.
@@ -262,10 +290,10 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     else if (t + 1 < T) load_step<C>(a, bt + 1, nxt);  // software prefetch of the next step's inputs
 
     float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
-    mix_A<C>(base, cur.al, row0, A);
-    mix_B<C>(base, cur.al, row0, Bm);
-    mix_Ct<C>(base, cur.al, row0, Ct);
-    mix_Q<C>(base, cur.al, row0, Q);
+    get_A<C>(a, base, cur.al, row0, bt, A);
+    get_B<C>(a, base, cur.al, row0, bt, Bm);
+    get_Ct<C>(a, base, cur.al, row0, bt, Ct);
+    get_Q<C>(a, base, cur.al, row0, bt, Q);
 
     // predict (A.1): mu_p = A mu + B u ; Sigma_p = (A Sigma) A^T + Q        (kalman_filter.py:65-67)
     float mup[R];
@@ -421,7 +449,8 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
         if (t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
       }
     } else {
-      load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
+      if (a.alpha) load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
+      else { KV_UNROLL for (int k = 0; k < C::K; ++k) al1[k] = 0.f; }
     }
     float Sf[R][N], Sp1[R][N], muf[R], mup1[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -431,7 +460,7 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     load_row<R>(a.mu_f + bt * N + row0, muf);
     load_row<R>(a.mu_p + (bt + 1) * N + row0, mup1);
     float A1[R][N];
-    mix_A<C>(base, al1, row0, A1);
+    get_A<C>(a, base, al1, row0, bt + 1, A1);
     float J[R][N], LU[R][N], invu[N];
     ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu) && ok;
     // mu_s = mu_f + J (mu_s1 - mu_p1)                                            (:232)

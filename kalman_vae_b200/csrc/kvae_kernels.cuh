@@ -50,7 +50,13 @@ __global__ void __launch_bounds__(TPB<C>) k_filter_smooth(Args a, BasePtrs bp, i
   const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
   float* stage_slot = tiles_all + (TPB<C> / 32) * FTiles<C>::warp_total + gi * InStage<C, true>::group_floats;
   float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
-  filter_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own);
+  if (a.smooth_only) {   // filtered states given: the belief at T-1 is the smoother's starting point
+    const long btl = (long)b * a.T + (a.T - 1);
+    for (int r = 0; r < C::R; ++r) load_row<C::N>(a.Sig_f + (btl * C::N + g.row0() + r) * C::N, Sig[r]);
+    load_row<C::R>(a.mu_f + btl * C::N + g.row0(), mu_own);
+  } else {
+    filter_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own);
+  }
   if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu_own);
 }
 

@@ -27,6 +27,8 @@ Args make_args(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st,
   a.mu_f = st.mus_filt; a.Sig_f = st.Sigmas_filt; a.mu_p = st.mus_pred; a.Sig_p = st.Sigmas_pred;
   a.mu_s = st.mus_smooth; a.Sig_s = st.Sigmas_smooth;
   a.mu_init = in.mu_init; a.Sig_init = in.Sigma_init;
+  a.dA = in.A_dense; a.dB = in.B_dense; a.dC = in.C_dense; a.dQ = in.Q_dense;
+  a.smooth_only = (d.flags & KVAE_FLAG_SMOOTH_ONLY) ? 1 : 0;
   a.info = info;
   return a;
 }

@@ -39,12 +39,14 @@ class Problem:
     lanes: int = 0
     mu_init: Optional[torch.Tensor] = None
     Sigma_init: Optional[torch.Tensor] = None
+    flags: int = 0
+    dense: Optional[tuple] = None      # (A [B,T,n,n], B [B,T,n,m], C [B,T,p,n], Q [B,T,n,n] | None): forward only
     dims: object = field(default=None, repr=False)
 
     def __post_init__(self):
         B, T, p = self.Y.shape
         K, n, m = self.Bm.shape
-        self.dims = capi.make_dims(B, T, n, p, m, K, self.q_per_mode, self.c_shared, self.lanes)
+        self.dims = capi.make_dims(B, T, n, p, m, K, self.q_per_mode, self.c_shared, self.lanes, self.flags)
         if not capi.supported(self.dims):
             raise capi.KvaeError(
                 f"shape (n={n}, p={p}, m={m}, K={K}, switching={self.q_per_mode}, lanes={self.lanes}) is not "
@@ -56,9 +58,10 @@ class Problem:
         return d.B, d.T, d.n, d.p, d.m, d.K
 
     def inputs(self, Y=None, U=None):
+        d = self.dense or (None, None, None, None)
         return capi.make_inputs(self.Y if Y is None else Y, self.U if U is None else U, self.mask, self.alpha,
                                 self.A, self.Bm, self.C, self.Q, self.R, self.mu0, self.Sigma0,
-                                self.mu_init, self.Sigma_init)
+                                self.mu_init, self.Sigma_init, d[0], d[1], d[2], d[3])
 
 
 def prep(t, device=None):

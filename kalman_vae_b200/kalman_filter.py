@@ -186,16 +186,20 @@ class KalmanFilter(nn.Module):
         mf, Sf, mp, Sp, A_list, B_list, C_list = (bt(x) for x in (mf, Sf, mp, Sp, Al, Bl, Cl))
         if not smooth:
             return mf, Sf, mp, Sp, A_list, B_list, C_list
-        # smoother sweep over the stored filter states: rerun the fused forward with the alphas now known
-        pb = self._problem(Y, U, mask_t, alpha, dyn.A, dyn.B, dyn.C, self.Q, False, False)
-        st, A_list, B_list, C_list = F.smooth_fwd(pb, smooth=True, lists=True)
+        # smoother sweep over the stored filter states (one launch, no refiltering)
+        pb = Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), prep(dyn.A, dev), prep(dyn.B, dev), prep(dyn.C, dev),
+                     prep(self.Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), False, False,
+                     lanes=self.lanes, flags=F.capi.FLAG_SMOOTH_ONLY)
+        st = States(mf, Sf, mp, Sp, torch.empty_like(mf), torch.empty_like(Sf))
+        F.capi.filter_smooth_fwd(pb.dims, pb.inputs(), st.c_struct(), None, None, None, F.info_word(dev), dev)
+        pb.flags = 0
+        pb.dims.flags = 0
         prov = _Provenance(pb, st, (Y, U, alpha, dyn.A, dyn.B, dyn.C, None), True)
         prov.mus_smooth_ref = weakref.ref(st.mus_smooth)
         prov.Sigmas_smooth_ref = weakref.ref(st.Sigmas_smooth)
         for t_ in (A_list, B_list, C_list):
             _tag(t_, prov)
-        return (st.mus_smooth, st.Sigmas_smooth, st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred,
-                A_list, B_list, C_list)
+        return (st.mus_smooth, st.Sigmas_smooth, mf, Sf, mp, Sp, A_list, B_list, C_list)
 
     def _ref_step_weights(self, a_tprev):
         dyn = self.dyn_params
@@ -251,25 +255,98 @@ class KalmanFilter(nn.Module):
         # y_t / u_t of this call are the same values as smooth()'s inputs (checked above): route the
         # gradient to the tensors the caller handed to elbo() AND smooth() by summing over both uses.
         y_in = y_t if y_t.requires_grad or not (Ys is not None and Ys.requires_grad) else Ys
-        jitter = 1e-6
         dev = y_t.device
-        if self.check_info:
-            F.info_word(dev).zero_()
-        val = F.FusedElboFunction.apply(pb, st, eps, jitter, extra, y_in, Us if Us is not None else None,
-                                        alpha, A, Bm, C, Q)
-        if self.check_info and int(F.info_word(dev).item()) != 0:
+        jitter = 1e-6
+        for attempt in range(5):                                                  # _safe_cholesky ladder (:291-296)
+            if self.check_info:
+                F.info_word(dev).zero_()
+            val = F.FusedElboFunction.apply(pb, st, eps, jitter, extra, y_in, Us if Us is not None else None,
+                                            alpha, A, Bm, C, Q)
+            if not self.check_info or int(F.info_word(dev).item()) == 0:
+                break
+            jitter *= 10.0      # a factorisation met a non-positive pivot: retry everything with 10x jitter
+        else:
             raise torch.linalg.LinAlgError(
-                "kvae elbo: a Cholesky factorisation met a non-positive pivot (the reference's "
-                "_safe_cholesky would retry with 10x jitter, kalman_filter.py:291-296)")
+                "kvae elbo: Cholesky failed for every jitter up to 1e-2 (the reference would fall back to the "
+                "clamped diagonal here, kalman_filter.py:298-302)")
         return val
 
     def _draw_eps(self, B, T, n, like):
         """The standard-normal draw behind MultivariateNormal.rsample (kalman_filter.py:351)."""
         return torch.empty(B, T, n, dtype=like.dtype, device=like.device).normal_()
 
-    def filter_step(self, mu_t_t, Sigma_t_t, y_t, u_t, A, B, C, Q, mask_t=None):
-        raise NotImplementedError("per-step form with explicit matrices: use filter() (single-step launches are "
-                                  "used internally for masked lstm dynamics)")
+    # ------------------------------------------------------------------ per-step forms (explicit matrices)
+    def _dense_problem(self, Y, U, mask, T, A, Bm, C, Q, mu_init=None, Sigma_init=None, flags=0):
+        """A forward launch that reads explicit per-step matrices [B,T,..] instead of mixing (forward only)."""
+        dev = Y.device
+        n, m, p = self.n, self.m, self.p
+        dyn = self.dyn_params
+        K = dyn.A.size(0)
+        sw = bool(dyn.is_switching_dynamics)
+        base_Q = dyn.Q if sw else self.Q
+        pb = Problem(prep(Y), prep(U), prep(mask), None, prep(dyn.A, dev), prep(dyn.B, dev), prep(dyn.C, dev),
+                     prep(base_Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), sw, sw,
+                     lanes=self.lanes, mu_init=prep(mu_init), Sigma_init=prep(Sigma_init), flags=flags,
+                     dense=(prep(A), prep(Bm), prep(C), prep(Q)))
+        return pb
 
-    def smooth_step(self, *a, **k):
-        raise NotImplementedError("per-step form: use smooth()")
+    def filter_step(self, mu_t_t, Sigma_t_t, y_t, u_t, A, B, C, Q, mask_t=None):
+        """kalman_filter.py:31-104 — one predict/update step with explicit per-sample matrices.
+        Returns (mu_t_t [B,n,1], Sigma_t_t, mu_t_tprev [B,n,1], Sigma_t_tprev, A, B, C).  Forward only."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (mu_t_t, Sigma_t_t, y_t, u_t, A, B, C)):
+            raise NotImplementedError("filter_step is forward-only here; differentiate through filter()/smooth()")
+        batch = y_t.size(0)
+        n, m, p = self.n, self.m, self.p
+        dev = y_t.device
+        f = lambda x, *shape: x.detach().to(torch.float32).expand(*shape).contiguous().view(*shape)
+        Qd = f(Q, batch, n, n).view(batch, 1, n, n)                                  # :35-36 (2-d Q is expanded)
+        if mask_t is None:
+            mask = None
+        else:
+            mk = mask_t.to(device=dev, dtype=torch.float32)
+            mask = (mk.expand(batch) if mk.dim() == 0 else mk).contiguous().view(batch, 1)   # :54-60
+        pb = self._dense_problem(y_t.reshape(batch, 1, p), u_t.reshape(batch, 1, m), mask, 1,
+                                 f(A, batch, n, n).view(batch, 1, n, n), f(B, batch, n, m).view(batch, 1, n, m),
+                                 f(C, batch, p, n).view(batch, 1, p, n), Qd,
+                                 mu_init=mu_t_t.reshape(batch, n), Sigma_init=f(Sigma_t_t, batch, n, n))
+        st, _, _, _ = F.smooth_fwd(pb, smooth=False, lists=False)
+        return (st.mus_filt.view(batch, n, 1), st.Sigmas_filt.view(batch, n, n), st.mus_pred.view(batch, n, 1),
+                st.Sigmas_pred.view(batch, n, n), A, B, C)
+
+    def smooth_step(self, Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, mu_t_t, mu_tpost_t, mu_tpost_T, A):
+        """kalman_filter.py:204-237 — one RTS step.  Returns (mu_t_T [B,n,1], Sigma_t_T).  Forward only."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, mu_t_t,
+                                                                     mu_tpost_t, mu_tpost_T, A)):
+            raise NotImplementedError("smooth_step is forward-only here; differentiate through smooth()")
+        batch = Sigma_t_t.size(0)
+        n, m, p = self.n, self.m, self.p
+        dev = Sigma_t_t.device
+        f32 = lambda x: x.detach().to(torch.float32)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        # a two-step "sequence": slot 0 = time t, slot 1 = time t+1.  The smoother sweep starts from the belief
+        # stored at the last FILTERED slot, so the smoothed belief at t+1 is placed there.
+        Sf = torch.stack([f32(Sigma_t_t), f32(Sigma_tpost_T)], 1).contiguous()
+        mf = torch.stack([f32(mu_t_t).reshape(batch, n), f32(mu_tpost_T).reshape(batch, n)], 1).contiguous()
+        Sp = torch.stack([z(batch, n, n), f32(Sigma_tpost_t)], 1).contiguous()
+        mp = torch.stack([z(batch, n), f32(mu_tpost_t).reshape(batch, n)], 1).contiguous()
+        Ad = torch.stack([z(batch, n, n), f32(A).expand(batch, n, n)], 1).contiguous()
+        pb = self._dense_problem(z(batch, 2, p), None, None, 2, Ad, z(batch, 2, n, m), z(batch, 2, p, n), None,
+                                 flags=F.capi.FLAG_SMOOTH_ONLY)
+        st = States(mf.view(batch, 2, n, 1), Sf, mp.view(batch, 2, n, 1), Sp, z(batch, 2, n, 1), z(batch, 2, n, n))
+        F.capi.filter_smooth_fwd(pb.dims, pb.inputs(), st.c_struct(), None, None, None, F.info_word(dev), dev)
+        return st.mus_smooth[:, 0].reshape(batch, n, 1), st.Sigmas_smooth[:, 0]
+
+    def _safe_cholesky(self, Sigma, max_tries=5, jitter_init=1e-6):
+        """kalman_filter.py:282-302 for callers that use it directly (the ELBO kernel factorises in-kernel):
+        chol(sym(Sigma) + jitter I) with the reference's 10x retry ladder and diagonal fallback."""
+        n = Sigma.size(-1)
+        Sigma = 0.5 * (Sigma + Sigma.mT)
+        eye = torch.eye(n, device=Sigma.device, dtype=Sigma.dtype)
+        jitter = jitter_init
+        for _ in range(max_tries):
+            L, info = torch.linalg.cholesky_ex(Sigma + jitter * eye)
+            if int(info.max()) == 0:
+                return L
+            jitter *= 10.0
+        diag = torch.clamp(torch.diagonal(Sigma, dim1=-2, dim2=-1), min=1e-6)
+        return torch.diag_embed(torch.sqrt(diag))

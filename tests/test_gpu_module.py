@@ -162,3 +162,61 @@ def test_kvae_imputation_recipe_matches_reference(kind, monkeypatch):
     a_filtered = (outs[8] @ outs[2]).squeeze(-1)                            # model.py:287-288
     assert torch.allclose(a_imputed.cpu(), g["a_imputed"], rtol=1e-4, atol=1e-6)
     assert torch.allclose(a_filtered.cpu(), g["a_filtered"], rtol=1e-4, atol=1e-6)
+
+
+def test_filter_step_and_smooth_step_match_reference_steps():
+    """Per-step forms (kalman_filter.py:31-104, :204-237) with explicit per-sample matrices, against the oracle's
+    step functions (same op sequence as the reference)."""
+    from oracle import kalman_oracle as ko
+    case, _, _, _ = load_golden("kalman_lstm")
+    kf, dyn = make_kf(case)
+    B, T, p = case["Y"].shape
+    n, m = kf.n, kf.m
+    gen = torch.Generator().manual_seed(3)
+    A = torch.eye(n).expand(B, n, n) + 0.1 * torch.randn(B, n, n, generator=gen)
+    Bm = 0.3 * torch.randn(B, n, m, generator=gen)
+    C = 0.3 * torch.randn(B, p, n, generator=gen)
+    L = torch.randn(B, n, n, generator=gen)
+    Sigma = L @ L.mT + 0.5 * torch.eye(n)
+    mu = torch.randn(B, n, generator=gen)
+    y, u = torch.randn(B, p, generator=gen), torch.randn(B, m, generator=gen)
+    mk = (torch.rand(B, generator=gen) > 0.3).float()
+    Q, R = case["Q"], case["R"]
+    ref = {dt: ko.filter_step(mu.to(dt).unsqueeze(-1), Sigma.to(dt), y.to(dt).unsqueeze(-1), u.to(dt).unsqueeze(-1), A.to(dt),
+                              Bm.to(dt), C.to(dt), Q.to(dt), R.to(dt).expand(B, -1, -1), mk.to(dt))
+           for dt in (torch.float32, torch.float64)}
+    d = lambda x: x.to(DEV)
+    with torch.no_grad():
+        out = kf.filter_step(d(mu), d(Sigma), d(y), d(u), d(A), d(Bm), d(C), d(Q), mask_t=d(mk))
+    assert len(out) == 7 and out[0].shape == (B, n, 1) and out[1].shape == (B, n, n)
+    for i, name in enumerate(("mu_f", "Sigma_f", "mu_p", "Sigma_p")):
+        check_close("filter_step." + name, out[i], ref[torch.float32][i], ref[torch.float64][i])
+    # smooth_step: t -> t+1 quantities from a second filter step
+    mu_f, Sig_f = ref[torch.float64][0], ref[torch.float64][1]
+    A1 = torch.eye(n).expand(B, n, n) + 0.1 * torch.randn(B, n, n, generator=gen)
+    Sig_p1 = A1.double() @ Sig_f @ A1.double().mT + Q.double()
+    mu_p1 = A1.double() @ mu_f
+    Sig_s1 = 0.7 * Sig_p1
+    Sig_s1 = 0.5 * (Sig_s1 + Sig_s1.mT)
+    mu_s1 = mu_p1 + 0.1
+    def ref_smooth(dt):
+        J = torch.linalg.solve(Sig_p1.to(dt).mT, (Sig_f.to(dt) @ A1.to(dt).mT).mT).mT
+        m_ = mu_f.to(dt) + J @ (mu_s1.to(dt) - mu_p1.to(dt))
+        S_ = Sig_f.to(dt) + J @ (Sig_s1.to(dt) - Sig_p1.to(dt)) @ J.mT
+        return m_, 0.5 * (S_ + S_.mT)
+    r32, r64 = ref_smooth(torch.float32), ref_smooth(torch.float64)
+    with torch.no_grad():
+        ms, Ss = kf.smooth_step(d(Sig_f.float()), d(Sig_p1.float()), d(Sig_s1.float()), d(mu_f.float()), d(mu_p1.float()),
+                                d(mu_s1.float()), d(A1))
+    assert ms.shape == (B, n, 1)
+    check_close("smooth_step.mu", ms, r32[0], r64[0])
+    check_close("smooth_step.Sigma", Ss, r32[1], r64[1])
+
+
+def test_safe_cholesky_matches_reference_ladder():
+    case = load_golden("kalman_lstm")[0]
+    kf, _ = make_kf(case)
+    S = torch.eye(4, device=DEV).expand(3, 4, 4).clone()
+    S[1, 0, 0] = -1e-4          # needs a larger jitter than 1e-6
+    L = kf._safe_cholesky(S)
+    assert torch.isfinite(L).all() and torch.allclose(L[0], torch.linalg.cholesky(torch.eye(4, device=DEV) * (1 + 1e-3)), atol=1e-6)
