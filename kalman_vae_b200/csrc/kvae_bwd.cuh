@@ -146,6 +146,36 @@ template <class C> struct GradAcc {
   }
 };
 
+// Everything sweep 3 reads from global memory for step t, fetched one step ahead (software prefetch):
+// the sweep is latency bound at small batch, and these L2 round trips would otherwise sit on its critical path.
+template <class C> struct S3In {
+  StepIn<C> in;                       // y_t, u_t, alpha_t, mask_t
+  float al1[C::K], u1[C::M];          // alpha_{t+1}, u_{t+1}
+  float eps1[C::N];                   // eps_{t+1}
+  float Ss1[C::R][C::N], ms1[C::R];   // Sigma_s, mu_s at t+1
+  float Sf[C::R][C::N];               // Sigma_f at t
+  float Sp1[C::R][C::N], mp1[C::R];   // Sigma_p, mu_p at t+1
+};
+template <class C> KV_FN void load_s3(const Args& a, long bt, bool has_next, bool has_elbo, int row0, S3In<C>& s) {
+  constexpr int N = C::N, M = C::M, K = C::K, R = C::R;
+  load_step<C>(a, bt, s.in);
+  KV_UNROLL for (int k = 0; k < K; ++k) s.al1[k] = 0.f;
+  KV_UNROLL for (int j = 0; j < M; ++j) s.u1[j] = 0.f;
+  KV_UNROLL for (int j = 0; j < N; ++j) s.eps1[j] = 0.f;
+  if (has_next) {
+    load_row<K>(a.alpha + (bt + 1) * K, s.al1);
+    if (a.U) load_row<M>(a.U + (bt + 1) * M, s.u1);
+    if (has_elbo) load_row<N>(a.eps + (bt + 1) * N, s.eps1);
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      load_row<N>(a.Sig_f + (bt * N + row0 + r) * N, s.Sf[r]);
+      load_row<N>(a.Sig_p + ((bt + 1) * N + row0 + r) * N, s.Sp1[r]);
+      load_row<N>(a.Sig_s + ((bt + 1) * N + row0 + r) * N, s.Ss1[r]);
+    }
+    load_row<R>(a.mu_s + (bt + 1) * N + row0, s.ms1);
+    load_row<R>(a.mu_p + (bt + 1) * N + row0, s.mp1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // sweep 3: ELBO adjoint (A.3) + smoother adjoint (A.4), forward in time
 // ---------------------------------------------------------------------------------------
@@ -199,18 +229,20 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     }
   }
 
+  S3In<C> pf;
+  load_s3<C>(a, (long)b * T, T > 1, has_elbo, row0, pf);
+  float eps_cur[N];    // eps_t (the previous step's eps_{t+1})
+  KV_UNROLL for (int j = 0; j < N; ++j) eps_cur[j] = 0.f;
+  if (has_elbo) load_row<N>(a.eps + (long)b * T * N, eps_cur);
   for (int t = 0; t < T; ++t) {
     const long bt = (long)b * T + t;
     const bool has_next = (t + 1 < T);
-    StepIn<C> in;
-    load_step<C>(a, bt, in);
+    const S3In<C> cu = pf;                                   // this step's inputs (fetched one step ago)
+    if (has_next) load_s3<C>(a, bt + 1, t + 2 < T, has_elbo, row0, pf);
+    const StepIn<C>& in = cu.in;
     float al1[K], u1[M];
-    KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = 0.f;
-    KV_UNROLL for (int j = 0; j < M; ++j) u1[j] = 0.f;
-    if (has_next) {
-      load_row<K>(a.alpha + (bt + 1) * K, al1);
-      if (a.U) load_row<M>(a.U + (bt + 1) * M, u1);
-    }
+    KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = cu.al1[k];
+    KV_UNROLL for (int j = 0; j < M; ++j) u1[j] = cu.u1[j];
     float A1[R][N];
     mix_A<C>(base, al1, row0, A1);
     float Ab[R][N], Bb[R][M], Qb[R][N], Ctb[R][P];   // (A,B,Q)-bar at t+1 and C^T-bar at t
@@ -239,9 +271,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
       float zbar_own[R];
       KV_UNROLL for (int r = 0; r < R; ++r) zbar_own[r] = xbar_own[r];
       if (has_next) {
-        float eps1[N];
-        load_row<N>(a.eps + (bt + 1) * N, eps1);
-        ok = elbo_sample_t<C>(a, g, T0, VB, bt + 1, w.jitter, eps1, es1) && ok;
+        ok = elbo_sample_rows<C>(g, T0, VB, cu.Ss1, cu.ms1, w.jitter, cu.eps1, es1) && ok;
         // x_{t+1} = z_{t+1} - A1 z_t - B1 u_{t+1};  q = Qj^-1 x;  xbar = -c q
         float B1[R][M];
         mix_B<C>(base, al1, row0, B1);
@@ -330,7 +360,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
       {
         float zbar[N], eps[N];
         allgather<MEM, L, R>(g, zbar_own, VB2, zbar);
-        load_row<N>(a.eps + bt * N, eps);
+        KV_UNROLL for (int j = 0; j < N; ++j) eps[j] = eps_cur[j];
         auto Ls_v = publish<MEM, L, R, N>(g, es.Ls, T1);
         float v_own[R];
         matTvec_own<C>(Ls_v, row0, zbar, v_own);
@@ -362,14 +392,11 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     load_vec_opt<R>(w.c_mu_f, bt * N + row0, mfb);
     float Ssb1[R][N], msb1[R];
     if (has_next) {
-      float Sf[R][N], Sp1[R][N], Ss1[R][N], ms1[R], mp1[R];
-      KV_UNROLL for (int r = 0; r < R; ++r) {
-        load_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);
-        load_row<N>(a.Sig_p + ((bt + 1) * N + row0 + r) * N, Sp1[r]);
-        load_row<N>(a.Sig_s + ((bt + 1) * N + row0 + r) * N, Ss1[r]);
-      }
-      load_row<R>(a.mu_s + (bt + 1) * N + row0, ms1);
-      load_row<R>(a.mu_p + (bt + 1) * N + row0, mp1);
+      const float (&Sf)[R][N] = cu.Sf;
+      const float (&Sp1)[R][N] = cu.Sp1;
+      const float (&Ss1)[R][N] = cu.Ss1;
+      const float (&ms1)[R] = cu.ms1;
+      const float (&mp1)[R] = cu.mp1;
       float J[R][N], LU[R][N], invu[N];
       ok = smoother_gain<C>(g, T0, T1, Sf, A1, Sp1, J, LU, invu) && ok;        // A1_v in T0, LU_v in T1
       typename view_of<MEM, L, R, N>::type A1_v, LU_v;
@@ -474,8 +501,40 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
       KV_UNROLL for (int j = 0; j < N; ++j) Ssb[r][j] = Ssb1[r][j];
     }
     if (has_elbo && has_next) es = es1;
+    KV_UNROLL for (int j = 0; j < N; ++j) eps_cur[j] = cu.eps1[j];
   }
   if (!ok && active) *a.info = 1;
+}
+
+// What sweep 4 reads from global memory for step t (prefetched one step ahead, as in sweep 3)
+template <class C> struct S4In {
+  StepIn<C> in;
+  float Sfb[C::R][C::N], mfb[C::R], Spb[C::R][C::N], mpb[C::R];   // scratch left by sweep 3
+  float Sp[C::R][C::N], mup[C::R];                               // Sigma_p, mu_p at t
+  float Sprev[C::R][C::N], muprev[C::N];                         // filtered belief at t-1 (or the initial one)
+};
+template <class C>
+KV_FN void load_s4(const Args& a, const BwdArgs& w, const float* base, int b, int t, int row0, S4In<C>& s) {
+  constexpr int N = C::N, R = C::R;
+  const long bt = (long)b * a.T + t;
+  load_step<C>(a, bt, s.in);
+  KV_UNROLL for (int r = 0; r < R; ++r) {
+    load_row<N>(w.w_Sig_f + (bt * N + row0 + r) * N, s.Sfb[r]);
+    load_row<N>(w.w_Sig_p + (bt * N + row0 + r) * N, s.Spb[r]);
+    load_row<N>(a.Sig_p + (bt * N + row0 + r) * N, s.Sp[r]);
+  }
+  load_row<R>(w.w_mu_f + bt * N + row0, s.mfb);
+  load_row<R>(w.w_mu_p + bt * N + row0, s.mpb);
+  load_row<R>(a.mu_p + bt * N + row0, s.mup);
+  if (t > 0) {
+    KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_f + ((bt - 1) * N + row0 + r) * N, s.Sprev[r]);
+    load_row<N>(a.mu_f + (bt - 1) * N, s.muprev);
+  } else {
+    if (a.Sig_init) { KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_init + ((long)b * N + row0 + r) * N, s.Sprev[r]); }
+    else copy_rows<C, N>(base + Base<C>::oS0, row0, s.Sprev);
+    if (a.mu_init) load_row<N>(a.mu_init + (long)b * N, s.muprev);
+    else load_row<N>(base + Base<C>::oMu0, s.muprev);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -496,32 +555,23 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
   float Sf_carry[R][N], mf_carry[R];
   KV_UNROLL for (int r = 0; r < R; ++r) { mf_carry[r] = 0.f; KV_UNROLL for (int j = 0; j < N; ++j) Sf_carry[r][j] = 0.f; }
 
+  S4In<C> pf;
+  load_s4<C>(a, w, base, b, T - 1, row0, pf);
   for (int t = T - 1; t >= 0; --t) {
     const long bt = (long)b * T + t;
-    StepIn<C> in;
-    load_step<C>(a, bt, in);
+    const S4In<C> cu = pf;                                   // this step's inputs (fetched one step ago)
+    if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf);
+    const StepIn<C>& in = cu.in;
     float Sfb[R][N], mfb[R], Spb[R][N], mpb[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
-      load_row<N>(w.w_Sig_f + (bt * N + row0 + r) * N, Sfb[r]);
-      load_row<N>(w.w_Sig_p + (bt * N + row0 + r) * N, Spb[r]);
+      KV_UNROLL for (int j = 0; j < N; ++j) { Sfb[r][j] = cu.Sfb[r][j] + Sf_carry[r][j]; Spb[r][j] = cu.Spb[r][j]; }
+      mfb[r] = cu.mfb[r] + mf_carry[r];
+      mpb[r] = cu.mpb[r];
     }
-    load_row<R>(w.w_mu_f + bt * N + row0, mfb);
-    load_row<R>(w.w_mu_p + bt * N + row0, mpb);
-    add_rows<R, N>(Sfb, Sf_carry);
-    KV_UNROLL for (int r = 0; r < R; ++r) mfb[r] += mf_carry[r];
-
-    float Sp[R][N], mup[R], Sprev[R][N], muprev[N];
-    KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_p + (bt * N + row0 + r) * N, Sp[r]);
-    load_row<R>(a.mu_p + bt * N + row0, mup);
-    if (t > 0) {
-      KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_f + ((bt - 1) * N + row0 + r) * N, Sprev[r]);
-      load_row<N>(a.mu_f + (bt - 1) * N, muprev);
-    } else {
-      if (a.Sig_init) { KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_init + ((long)b * N + row0 + r) * N, Sprev[r]); }
-      else copy_rows<C, N>(base + Base<C>::oS0, row0, Sprev);
-      if (a.mu_init) load_row<N>(a.mu_init + (long)b * N, muprev);
-      else load_row<N>(base + Base<C>::oMu0, muprev);
-    }
+    const float (&Sp)[R][N] = cu.Sp;
+    const float (&mup)[R] = cu.mup;
+    const float (&Sprev)[R][N] = cu.Sprev;
+    const float (&muprev)[N] = cu.muprev;
     float A[R][N], Bm[R][M], Ct[R][P];
     mix_A<C>(base, in.al, row0, A);
     mix_B<C>(base, in.al, row0, Bm);

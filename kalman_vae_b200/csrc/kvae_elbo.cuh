@@ -61,15 +61,12 @@ template <class C> struct ElboStep {
   float z[C::N];          // replicated sample
 };
 
-// z_t for one step: loads Sigma_s / mu_s at index bt (xbuf: [N x N] tile, vbuf: N-vector slot)
+// z_t from the lane's rows of Sigma_s and entries of mu_s (xbuf: [N x N] tile, vbuf: N-vector slot)
 template <class C>
-KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, long bt, float jitter,
-                         const float (&eps)[C::N], ElboStep<C>& es) {
+KV_FN bool elbo_sample_rows(const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, const float (&Ss)[C::R][C::N],
+                            const float (&mus)[C::R], float jitter, const float (&eps)[C::N], ElboStep<C>& es) {
   constexpr int N = C::N, R = C::R;
-  const int row0 = g.row0();
-  float Ss[R][N], Sj[R][N], mus[R];
-  KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Ss[r]);
-  load_row<R>(a.mu_s + bt * N + row0, mus);
+  float Sj[R][N];
   sym_jitter_rows<C>(g, Ss, xbuf, jitter, Sj);                         // (:287, :293)
   const bool ok = chol_dist<C::L, R>(g, Sj, es.Ls, es.invd, es.dg);
   KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -79,6 +76,17 @@ KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf
   }
   allgather<C::MEM, C::L, R>(g, es.z_own, vbuf, es.z);
   return ok;
+}
+// same, loading Sigma_s / mu_s at index bt
+template <class C>
+KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, long bt, float jitter,
+                         const float (&eps)[C::N], ElboStep<C>& es) {
+  constexpr int N = C::N, R = C::R;
+  const int row0 = g.row0();
+  float Ss[R][N], mus[R];
+  KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Ss[r]);
+  load_row<R>(a.mu_s + bt * N + row0, mus);
+  return elbo_sample_rows<C>(g, xbuf, vbuf, Ss, mus, jitter, eps, es);
 }
 
 // ELBO terms of time steps [t0, t1) of sequence b (the steps are independent given z_{t0-1}, which is

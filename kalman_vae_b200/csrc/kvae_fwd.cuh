@@ -409,6 +409,19 @@ KV_FN bool smoother_gain(const Group<C::L, C::R>& g, TileRef XA, TileRef XL, con
   return ok;
 }
 
+// states a smoother step reads: Sigma_f/mu_f at t and Sigma_p/mu_p at t+1 (own rows / entries)
+template <class C> struct SmoothIn {
+  float Sf[C::R][C::N], Sp1[C::R][C::N], muf[C::R], mup1[C::R];
+};
+template <class C> KV_FN void load_smooth_in(const Args& a, long bt, int row0, SmoothIn<C>& s) {
+  KV_UNROLL for (int r = 0; r < C::R; ++r) {
+    load_row<C::N>(a.Sig_f + (bt * C::N + row0 + r) * C::N, s.Sf[r]);
+    load_row<C::N>(a.Sig_p + ((bt + 1) * C::N + row0 + r) * C::N, s.Sp1[r]);
+  }
+  load_row<C::R>(a.mu_f + bt * C::N + row0, s.muf);
+  load_row<C::R>(a.mu_p + (bt + 1) * C::N + row0, s.mup1);
+}
+
 // ---------------------------------------------------------------------------------------
 // sweep 2: RTS smoother, t = T-2..0.  Sig / mus (own rows / entries) enter as the last filtered
 // belief (= smoothed belief at T-1).
@@ -437,6 +450,8 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     ins.commit(g);
     if (T >= 8) ins.prefetch(a, g, (long)b * T + (T - 8));
   }
+  SmoothIn<C> pf;   // software prefetch: the states of the step after the current one
+  if (T >= 2) load_smooth_in<C>(a, (long)b * T + (T - 2), row0, pf);
   for (int t = T - 2; t >= 0; --t) {
     const long bt = (long)b * T + t;
     float al1[C::K];
@@ -452,13 +467,13 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       if (a.alpha) load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
       else { KV_UNROLL for (int k = 0; k < C::K; ++k) al1[k] = 0.f; }
     }
+    // this step's states were fetched one iteration ago; start fetching the next step's now
     float Sf[R][N], Sp1[R][N], muf[R], mup1[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
-      load_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);
-      load_row<N>(a.Sig_p + ((bt + 1) * N + row0 + r) * N, Sp1[r]);
+      KV_UNROLL for (int j = 0; j < N; ++j) { Sf[r][j] = pf.Sf[r][j]; Sp1[r][j] = pf.Sp1[r][j]; }
+      muf[r] = pf.muf[r]; mup1[r] = pf.mup1[r];
     }
-    load_row<R>(a.mu_f + bt * N + row0, muf);
-    load_row<R>(a.mu_p + (bt + 1) * N + row0, mup1);
+    if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
     float A1[R][N];
     get_A<C>(a, base, al1, row0, bt + 1, A1);
     float J[R][N], LU[R][N], invu[N];
