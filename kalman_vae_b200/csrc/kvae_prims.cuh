@@ -28,6 +28,18 @@
 
 namespace kvae {
 
+// reciprocal square root to ~1 ulp: hardware approximation (MUFU.RSQ, 2 ulp) + one Newton step; one
+// special-function op on the critical path of a Cholesky pivot instead of sqrt followed by a reciprocal
+KV_FN float kv_rsqrt(float s) {
+#if defined(__CUDA_ARCH__)
+  const float y0 = rsqrtf(s);
+  const float e = fmaf(-s * y0, y0, 1.0f);
+  return fmaf(0.5f * y0, e, y0);
+#else
+  return 1.0f / sqrtf(s);
+#endif
+}
+
 struct alignas(16) f4 { float x, y, z, w; };
 struct alignas(8) f2 { float x, y; };
 
@@ -286,9 +298,9 @@ template <int D> KV_FN bool chol_small(const float (&a)[D][D], float (&l)[D][D],
     float s = a[j][j];
     KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-l[j][q], l[j][q], s);
     ok = ok && (s > 0.f);
-    const float d = sqrtf(s);
+    invd[j] = kv_rsqrt(s);
+    const float d = s * invd[j];
     l[j][j] = d;
-    invd[j] = 1.0f / d;
     KV_UNROLL for (int i = j + 1; i < D; ++i) {
       float v = a[i][j];
       KV_UNROLL for (int q = 0; q < j; ++q) v = fmaf(-l[i][q], l[j][q], v);
@@ -316,8 +328,8 @@ KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l
     float s = g.bcast(a[jr][j], owner);
     KV_UNROLL for (int q = 0; q < j; ++q) s = fmaf(-lj[q], lj[q], s);
     ok = ok && (s > 0.f);
-    const float d = sqrtf(s);
-    invd[j] = 1.0f / d;
+    invd[j] = kv_rsqrt(s);
+    const float d = s * invd[j];
     KV_UNROLL for (int r = 0; r < R; ++r) {
       const int i = g.row0() + r;
       float v = a[r][j];
