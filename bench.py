@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -138,9 +138,9 @@ def run_reference(args, rank, world):
     t1 = time.perf_counter()
     ko.smooth_elbo_fwd_bwd(calib, torch.float32, backward=True)
     per_seq = (time.perf_counter() - t1) / 512
-    budget = 120.0
-    sample_B = int(min(shape.B, max(256, budget / ((args.steps + args.warmup) * per_seq))))
-    sample_B = max(256, (sample_B // 256) * 256)
+    budget = 170.0
+    sample_B = int(min(shape.B, max(1024, budget / ((args.steps + args.warmup) * per_seq))))
+    sample_B = max(1024, (sample_B // 256) * 256)
     case = make_case(Shape(sample_B, shape.T, shape.n, shape.p, shape.m, shape.K), seed=10)
     for _ in range(args.warmup):
         ko.smooth_elbo_fwd_bwd(case, torch.float32, backward=True)
@@ -209,12 +209,12 @@ def run_cuda(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     stream = torch.cuda.current_stream(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # samples through warm-up, the timed region and the per-kernel timing (all under load)
     for i in range(max(args.warmup, 3)):
         sets[i % nsets].step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -230,7 +230,7 @@ def run_cuda(args, rank, local_rank, world):
     value = world * shape.B * shape.T / (ms_step * 1e-3)
 
     # ---- per-kernel durations (CUDA events around each C-ABI call, rotating sets), for the roofline
-    def time_call(fn_name, reps=20):
+    def time_call(fn_name, reps=200):
         evs = []
         for i in range(3):
             getattr(sets[i % nsets], fn_name)()
@@ -328,7 +328,10 @@ def run_cuda(args, rank, local_rank, world):
                        "sharding": "batch dimension, contiguous per rank; ONE all-reduce per step of a flat buffer [parameter gradients | 5 ELBO sums]"},
             "e2e": e2e, "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_bwd launch at this workload from the
+                         # committed ncu --set full capture (profiles/r01d_ncu_full_summary_cfg2.csv); null for other kernels
+                         "traffic": 53.8e6 if dom.startswith("k_bwd") else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_seq_step": ab, "kernel_seconds": kt,
                          "whole_step_frac": ab["total"] * world * shape.B * shape.T / (ms_step * 1e-3) / 1e9 / (peak * world)},
             "cpu_baseline": cpu, "clocks": clocks,
@@ -341,8 +344,8 @@ def run_cuda(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--buffer-sets", type=int, default=6)

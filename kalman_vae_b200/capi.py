@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkvae_kalman.so")
+LIB_PATH = os.environ.get("KVAE_LIB") or os.path.join(_HERE, "libkvae_kalman.so")   # KVAE_LIB: development A/B builds
 
 
 class KvaeDims(Structure):

@@ -10,7 +10,10 @@
 namespace kvae {
 
 // threads per CTA: 4 warps; 2 warps for the large-state shapes (their per-warp tiles are big)
-template <class C> constexpr int TPB = (C::N >= 16) ? 64 : 128;
+#ifndef KV_TPB_SMALL
+#define KV_TPB_SMALL 128
+#endif
+template <class C> constexpr int TPB = (C::N >= 16) ? 64 : KV_TPB_SMALL;
 
 struct BasePtrs { const float *A, *Bm, *C, *Q, *R, *mu0, *S0; };
 
