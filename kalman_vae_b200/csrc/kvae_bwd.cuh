@@ -62,12 +62,6 @@ template <int R> KV_FN void load_vec_opt(const float* p, long off, float (&dst)[
 // Parameter-gradient accumulators held in registers (A.0 adjoint):
 //   dA_k += alpha_k Abar_t ... ; returns the partial <Abar_t, A_k> + ... for dalpha.
 // ---------------------------------------------------------------------------------------
-#if defined(__CUDA_ARCH__)
-#define KV_ATOMIC_ADD(p, v) atomicAdd((p), (v))
-#else
-#define KV_ATOMIC_ADD(p, v) (*(p) += (v))
-#endif
-
 template <class C> struct GradAcc {
   static constexpr int K = C::K, R = C::R, N = C::N, M = C::M, P = C::P;
   static constexpr int KQ = C::QPM ? C::K : 0;
@@ -76,22 +70,24 @@ template <class C> struct GradAcc {
   // flat parameter layout of the reduced gradient: dA [K][N][N] | dB [K][N][M] | dC [K][P][N] | dQ [K][N][N]
   static constexpr int fA = 0, fB = K * N * N, fC = fB + K * N * M, fQ = fC + K * P * N;
   static constexpr int PSZ = fQ + KQ * N * N;
-  // One register accumulator per (mode,row,col) element of the lane's rows.  For n = 16 that is 392 floats
-  // per lane and spills to local memory; the alternative kept below (SM: a per-CTA shared-memory accumulator
-  // updated with atomics) was measured 2.2x SLOWER on B200 (cfg4/8: 73.8 ms vs 32.8 ms), so it is off.
-  // The planned fix is a dense per-step store + a separate mode-contraction kernel.
-  static constexpr bool SM = false;
-  float v[SM ? 1 : count];
-  float* sacc;  // SM mode: [PSZ] floats in shared memory, zeroed by the kernel
-  bool on;      // SM mode: false for tail groups that mirror a valid sequence (they must not contribute)
+  // Small shapes: one register accumulator per (mode,row,col) element of the lane's rows (42 floats at n=4, L=4).
+  // Large shapes (n=16: 392 floats per lane): DENSE — the lane stores its rows of the per-step cotangents
+  // Abar_t/Bbar_t/Qbar_t(/Cbar_t^T) into dense scratch [B,T,..] (sweep 3 stores, sweep 4 adds) and a separate
+  // contraction kernel forms dA_k = sum_{b,t} alpha_{b,t,k} Abar_{b,t} etc.; only a shared C keeps registers.
+  // (A shared-memory atomic accumulator was measured 2.2x slower than even the spilling register version.)
+  static constexpr bool DENSE = count > 128;
+  static constexpr int nreg = DENSE ? (C::CSH ? R * P : 1) : count;
+  float v[nreg];
+  float *dnA, *dnB, *dnQ, *dnCt;   // DENSE: [B,T,N,N], [B,T,N,M], [B,T,N,N], [B,T,N,P] scratch
+  bool on;                         // false for tail groups that mirror a valid sequence (they must not store)
 
   KV_FN void zero() {
-    KV_UNROLL for (int i = 0; i < (SM ? 1 : count); ++i) v[i] = 0.f;
+    KV_UNROLL for (int i = 0; i < nreg; ++i) v[i] = 0.f;
   }
-  // dal[k] += <Xbar, X_k> over own rows (caller all-reduces); acc_k += al[k] * Xbar
-  // OFF: register offset of the block, FOFF: flat offset, TR: block is stored transposed in the flat layout (C^T)
-  template <int COLS, int OFF, int FOFF, bool TR, int MODES>
-  KV_FN void one(const float* basek, int row0, const float (&al)[K], const float (&Xb)[R][COLS], float (&dal)[K]) {
+  // dal[k] += <Xbar, X_k> over own rows (caller all-reduces); acc_k += al[k] * Xbar  (or dense store / add)
+  template <int COLS, int OFF, int MODES>
+  KV_FN void one(const float* basek, float* dense, int row0, const float (&al)[K], const float (&Xb)[R][COLS], float (&dal)[K],
+                 long bt, bool first) {
     KV_UNROLL for (int k = 0; k < MODES; ++k) {
       float s = 0.f;
       KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -99,39 +95,61 @@ template <class C> struct GradAcc {
         load_row<COLS>(basek + (k * N + row0 + r) * COLS, row);
         KV_UNROLL for (int j = 0; j < COLS; ++j) {
           s = fmaf(Xb[r][j], row[j], s);
-          if constexpr (SM) {
-            const int flat = TR ? FOFF + (k * COLS + j) * N + row0 + r : FOFF + (k * N + row0 + r) * COLS + j;
-            if (on) KV_ATOMIC_ADD(sacc + flat, al[k] * Xb[r][j]);
-          } else {
-            v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
-          }
+          if constexpr (!DENSE) v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
         }
       }
       dal[k] += s;
     }
-  }
-  KV_FN void addA(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K]) {
-    one<N, oA, fA, false, K>(base + Base<C>::oA, row0, al, Xb, dal);
-  }
-  KV_FN void addB(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][M], float (&dal)[K]) {
-    one<M, oB, fB, false, K>(base + Base<C>::oB, row0, al, Xb, dal);
-  }
-  KV_FN void addQ(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K]) {
-    if constexpr (C::QPM) one<N, oQ, fQ, false, K>(base + Base<C>::oQ, row0, al, Xb, dal);
-  }
-  KV_FN void addCt(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][P], float (&dal)[K]) {
-    if constexpr (C::CSH) {
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) {
-        if constexpr (SM) { if (on) KV_ATOMIC_ADD(sacc + fC + j * N + row0 + r, Xb[r][j]); }
-        else v[oCt + r * P + j] += Xb[r][j];
+    if constexpr (DENSE) {
+      if (on) {
+        KV_UNROLL for (int r = 0; r < R; ++r) {
+          float* dst = dense + (bt * N + row0 + r) * COLS;
+          if (first) store_row<COLS>(dst, Xb[r]);
+          else {
+            float cur[COLS];
+            load_row<COLS>(dst, cur);
+            KV_UNROLL for (int j = 0; j < COLS; ++j) cur[j] += Xb[r][j];
+            store_row<COLS>(dst, cur);
+          }
+        }
       }
+    } else { (void)dense; (void)bt; (void)first; }
+  }
+  KV_FN void addA(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K], long bt, bool first) {
+    one<N, oA, K>(base + Base<C>::oA, dnA, row0, al, Xb, dal, bt, first);
+  }
+  KV_FN void addB(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][M], float (&dal)[K], long bt, bool first) {
+    one<M, oB, K>(base + Base<C>::oB, dnB, row0, al, Xb, dal, bt, first);
+  }
+  KV_FN void addQ(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K], long bt, bool first) {
+    if constexpr (C::QPM) one<N, oQ, K>(base + Base<C>::oQ, dnQ, row0, al, Xb, dal, bt, first);
+  }
+  KV_FN void addCt(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][P], float (&dal)[K], long bt, bool first) {
+    if constexpr (C::CSH) {
+      constexpr int o = DENSE ? 0 : oCt;
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) v[o + r * P + j] += Xb[r][j];
     } else {
-      one<P, oCt, fC, true, K>(base + Base<C>::oCt, row0, al, Xb, dal);
+      one<P, oCt, K>(base + Base<C>::oCt, dnCt, row0, al, Xb, dal, bt, first);
     }
   }
-  // f(flat parameter index, value) for every register accumulator of the lane owning rows row0.. (register mode)
+  // zero the dense A/B/Q cotangents of step index bt (t = 0 receives nothing from sweep 3)
+  KV_FN void dense_zero_abq(int row0, long bt) {
+    if constexpr (DENSE) {
+      if (on) {
+        float zn[N], zm[M];
+        KV_UNROLL for (int j = 0; j < N; ++j) zn[j] = 0.f;
+        KV_UNROLL for (int j = 0; j < M; ++j) zm[j] = 0.f;
+        KV_UNROLL for (int r = 0; r < R; ++r) {
+          store_row<N>(dnA + (bt * N + row0 + r) * N, zn);
+          store_row<M>(dnB + (bt * N + row0 + r) * M, zm);
+          if constexpr (C::QPM) store_row<N>(dnQ + (bt * N + row0 + r) * N, zn);
+        }
+      }
+    } else { (void)row0; (void)bt; }
+  }
+  // f(flat parameter index, value) for every register accumulator of the lane owning rows row0..
   template <class F> KV_FN void for_each(int row0, F&& f) const {
-    if constexpr (!SM) {
+    if constexpr (!DENSE) {
       KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
         f(fA + (k * N + row0 + r) * N + j, v[oA + (k * R + r) * N + j]);
       KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < M; ++j)
@@ -142,8 +160,11 @@ template <class C> struct GradAcc {
         KV_UNROLL for (int k = 0; k < K; ++k) KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
           f(fQ + (k * N + row0 + r) * N + j, v[oQ + (k * R + r) * N + j]);
       }
+    } else if constexpr (C::CSH) {
+      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) f(fC + j * N + row0 + r, v[r * P + j]);
     } else { (void)row0; (void)f; }
   }
+  static constexpr int nreduce = DENSE ? (C::CSH ? R * P : 0) : count;   // register accumulators to reduce per CTA
 };
 
 // Everything sweep 3 reads from global memory for step t, fetched one step ahead (software prefetch):
@@ -229,16 +250,19 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     }
   }
 
+  // software prefetch only for small states: for n = 16 the second copy of the per-step inputs would spill
+  constexpr bool PF = (C::N <= 8);
   S3In<C> pf;
-  load_s3<C>(a, (long)b * T, T > 1, has_elbo, row0, pf);
+  if constexpr (PF) load_s3<C>(a, (long)b * T, T > 1, has_elbo, row0, pf);
   float eps_cur[N];    // eps_t (the previous step's eps_{t+1})
   KV_UNROLL for (int j = 0; j < N; ++j) eps_cur[j] = 0.f;
   if (has_elbo) load_row<N>(a.eps + (long)b * T * N, eps_cur);
   for (int t = 0; t < T; ++t) {
     const long bt = (long)b * T + t;
     const bool has_next = (t + 1 < T);
-    const S3In<C> cu = pf;                                   // this step's inputs (fetched one step ago)
-    if (has_next) load_s3<C>(a, bt + 1, t + 2 < T, has_elbo, row0, pf);
+    if constexpr (!PF) load_s3<C>(a, bt, has_next, has_elbo, row0, pf);
+    const S3In<C> cu = pf;                                   // this step's inputs (PF: fetched one step ago)
+    if constexpr (PF) { if (has_next) load_s3<C>(a, bt + 1, t + 2 < T, has_elbo, row0, pf); }
     const StepIn<C>& in = cu.in;
     float al1[K], u1[M];
     KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = cu.al1[k];
@@ -473,11 +497,12 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     float dal_next[K], dal_c[K];
     KV_UNROLL for (int k = 0; k < K; ++k) { dal_next[k] = 0.f; dal_c[k] = 0.f; }
     if (has_next) {
-      acc.addA(base, row0, al1, Ab, dal_next);
-      acc.addB(base, row0, al1, Bb, dal_next);
-      acc.addQ(base, row0, al1, Qb, dal_next);
+      acc.addA(base, row0, al1, Ab, dal_next, bt + 1, true);
+      acc.addB(base, row0, al1, Bb, dal_next, bt + 1, true);
+      acc.addQ(base, row0, al1, Qb, dal_next, bt + 1, true);
     }
-    acc.addCt(base, row0, in.al, Ctb, dal_c);
+    if (t == 0) acc.dense_zero_abq(row0, bt);
+    acc.addCt(base, row0, in.al, Ctb, dal_c, bt, true);
     float red[2 * K + M];
     KV_UNROLL for (int k = 0; k < K; ++k) { red[k] = dal_next[k]; red[K + k] = dal_c[k]; }
     KV_UNROLL for (int j = 0; j < M; ++j) red[2 * K + j] = du1[j];
@@ -555,12 +580,14 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
   float Sf_carry[R][N], mf_carry[R];
   KV_UNROLL for (int r = 0; r < R; ++r) { mf_carry[r] = 0.f; KV_UNROLL for (int j = 0; j < N; ++j) Sf_carry[r][j] = 0.f; }
 
+  constexpr bool PF = (C::N <= 8);
   S4In<C> pf;
-  load_s4<C>(a, w, base, b, T - 1, row0, pf);
+  if constexpr (PF) load_s4<C>(a, w, base, b, T - 1, row0, pf);
   for (int t = T - 1; t >= 0; --t) {
     const long bt = (long)b * T + t;
-    const S4In<C> cu = pf;                                   // this step's inputs (fetched one step ago)
-    if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf);
+    if constexpr (!PF) load_s4<C>(a, w, base, b, t, row0, pf);
+    const S4In<C> cu = pf;                                   // this step's inputs (PF: fetched one step ago)
+    if constexpr (PF) { if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf); }
     const StepIn<C>& in = cu.in;
     float Sfb[R][N], mfb[R], Spb[R][N], mpb[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -726,10 +753,10 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
     // A.0: contract with the base matrices
     float dal[K];
     KV_UNROLL for (int k = 0; k < K; ++k) dal[k] = 0.f;
-    acc.addA(base, row0, in.al, Ab, dal);
-    acc.addB(base, row0, in.al, Bb, dal);
-    acc.addQ(base, row0, in.al, Spb, dal);
-    acc.addCt(base, row0, in.al, Ctb, dal);
+    acc.addA(base, row0, in.al, Ab, dal, bt, false);
+    acc.addB(base, row0, in.al, Bb, dal, bt, false);
+    acc.addQ(base, row0, in.al, Spb, dal, bt, false);
+    acc.addCt(base, row0, in.al, Ctb, dal, bt, false);
     float red2[K + M];
     KV_UNROLL for (int k = 0; k < K; ++k) red2[k] = dal[k];
     KV_UNROLL for (int j = 0; j < M; ++j) red2[K + j] = du[j];

@@ -202,10 +202,10 @@ template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitt
 // second kernel sums the per-CTA partials.
 // ------------------------------------------------------------------------------------------------
 struct GradPtrs { float *dA, *dB, *dC, *dQ; };
+struct DensePtrs { float *A, *B, *Q, *Ct; };
 
 template <class C> constexpr size_t smem_floats_bwd() {
   constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(TPB<C> / 32) * BTiles<C>::warp_total;
-  if (GradAcc<C>::SM) return tiles + (size_t)GradAcc<C>::PSZ;   // accumulator lives beside the tiles
   constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
   return tiles > red ? tiles : red;
 }
@@ -215,32 +215,51 @@ template <class C> constexpr size_t smem_floats_bwd() {
 template <class C>
 __device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L, C::R>& g, bool active, float* red,
                                                float* __restrict__ partial_row) {
-  if constexpr (GradAcc<C>::SM) {   // already accumulated per CTA in shared memory (inactive groups added nothing)
-    (void)g; (void)active; (void)red;
-    __syncthreads();
-    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = acc.sacc[i];
-  } else {
-    if (!active) acc.zero();
+  if (!active) acc.zero();
 #pragma unroll
-    for (int off = C::L; off < 32; off <<= 1) {
+  for (int off = C::L; off < 32; off <<= 1) {
 #pragma unroll
-      for (int i = 0; i < GradAcc<C>::count; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
-    }
-    __syncthreads();   // tiles are dead: reuse them
-    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int wq = 0; wq < TPB<C> / 32; ++wq) {
-      if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
-      __syncthreads();
-    }
-    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
+    for (int i = 0; i < GradAcc<C>::nreduce; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
   }
+  __syncthreads();   // tiles are dead: reuse them
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int wq = 0; wq < TPB<C> / 32; ++wq) {
+    if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
+}
+
+// DENSE gradient mode: out[k][e] = sum_{bt in chunk} alpha[bt][k] * X[bt][e]  (one thread per column e, K register
+// accumulators, X streamed once with coalesced loads); partial rows are reduced by k_param_final.
+template <int K>
+static __global__ void __launch_bounds__(256) k_mode_contract(const float* __restrict__ alpha, const float* __restrict__ X, long BT,
+                                                              int E, int chunk, float* __restrict__ rows, int psz, int foff,
+                                                              int transposeP, int Ncols) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= E) return;
+  const long bt0 = (long)blockIdx.y * chunk;
+  const long bt1 = bt0 + chunk < BT ? bt0 + chunk : BT;
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  for (long bt = bt0; bt < bt1; ++bt) {
+    const float x = X[bt * E + e];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = fmaf(alpha[bt * K + k], x, acc[k]);
+  }
+  // flat index: row-major [k][e], or for the transposed C^T scratch ([N][P] per step -> dC [k][P][N]) swap (i,a)
+  int fe = e;
+  if (transposeP) { const int i = e / transposeP, a_ = e % transposeP; fe = a_ * Ncols + i; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) rows[(size_t)blockIdx.y * psz + foff + k * E + fe] = acc[k];
 }
 
 template <class C>
 __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
-                                                  const float* __restrict__ terms, float* __restrict__ partials) {
+                                                  const float* __restrict__ terms, float* __restrict__ partials, DensePtrs dn) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
@@ -254,13 +273,8 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   w.c_elbo = g_elbo ? (*g_elbo) * terms[6] : 0.f;
   GradAcc<C> acc;
   acc.zero();
-  acc.sacc = nullptr;
   acc.on = active;
-  if constexpr (GradAcc<C>::SM) {
-    acc.sacc = tiles_all + (TPB<C> / 32) * BTiles<C>::warp_total;
-    for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) acc.sacc[i] = 0.f;
-    __syncthreads();
-  }
+  acc.dnA = dn.A; acc.dnB = dn.B; acc.dnQ = dn.Q; acc.dnCt = dn.Ct;
   bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
   bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
   cta_reduce_acc<C>(acc, g, active, tiles_all, partials + (size_t)blockIdx.x * GradAcc<C>::PSZ);
@@ -287,40 +301,81 @@ static __global__ void k_param_final(const float* __restrict__ partials, int nbl
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+template <class C> inline int contract_chunks(long BT) {
+  long n = BT / 256;
+  if (n < 1) n = 1;
+  if (n > 592) n = 592;
+  return (int)n;
+}
 template <class C> size_t bwd_ws_bytes(int B, int T) {
   constexpr int GPB = TPB<C> / C::L;
-  const size_t nn = align256(sizeof(float) * (size_t)B * T * C::N * C::N);
-  const size_t nv = align256(sizeof(float) * (size_t)B * T * C::N);
-  const size_t rows = (size_t)((B + GPB - 1) / GPB);
-  return 2 * nn + 2 * nv + align256(sizeof(float) * rows * GradAcc<C>::PSZ);
+  using GA = GradAcc<C>;
+  const size_t BT = (size_t)B * T;
+  const size_t nn = align256(sizeof(float) * BT * C::N * C::N);
+  const size_t nv = align256(sizeof(float) * BT * C::N);
+  size_t rows = (size_t)((B + GPB - 1) / GPB);
+  size_t dense = 0;
+  if (GA::DENSE) {
+    rows += (size_t)contract_chunks<C>((long)BT);
+    dense = nn + align256(sizeof(float) * BT * C::N * C::M) + (C::QPM ? nn : 0) +
+            (C::CSH ? 0 : align256(sizeof(float) * BT * C::N * C::P));
+  }
+  return 2 * nn + 2 * nv + dense + align256(sizeof(float) * rows * GA::PSZ);
 }
 
 template <class C>
 int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo, const float* terms, void* ws,
                GradPtrs gp, cudaStream_t s) {
   constexpr int GPB = TPB<C> / C::L;
+  using GA = GradAcc<C>;
   const size_t sm = sizeof(float) * smem_floats_bwd<C>();
   static bool attr_set = false;
+  (void)cudaGetLastError();
   if (sm > 48 * 1024 && !attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const size_t nn = align256(sizeof(float) * (size_t)a.B * a.T * C::N * C::N);
-  const size_t nv = align256(sizeof(float) * (size_t)a.B * a.T * C::N);
+  const size_t BT = (size_t)a.B * a.T;
+  const size_t nn = align256(sizeof(float) * BT * C::N * C::N);
+  const size_t nv = align256(sizeof(float) * BT * C::N);
   char* p = reinterpret_cast<char*>(ws);
   w.w_Sig_f = reinterpret_cast<float*>(p); p += nn;
   w.w_Sig_p = reinterpret_cast<float*>(p); p += nn;
   w.w_mu_f = reinterpret_cast<float*>(p); p += nv;
   w.w_mu_p = reinterpret_cast<float*>(p); p += nv;
+  DensePtrs dn{nullptr, nullptr, nullptr, nullptr};
+  if (GA::DENSE) {
+    dn.A = reinterpret_cast<float*>(p); p += nn;
+    dn.B = reinterpret_cast<float*>(p); p += align256(sizeof(float) * BT * C::N * C::M);
+    if (C::QPM) { dn.Q = reinterpret_cast<float*>(p); p += nn; }
+    if (!C::CSH) { dn.Ct = reinterpret_cast<float*>(p); p += align256(sizeof(float) * BT * C::N * C::P); }
+  }
   float* partials = reinterpret_cast<float*>(p);
-  constexpr int psz = GradAcc<C>::PSZ;
+  constexpr int psz = GA::PSZ;
   const int grid = (a.B + GPB - 1) / GPB;
   constexpr int tpb = TPB<C>;
-  k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials);
+  k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials, dn);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, grid, psz, C::K * C::N * C::N, C::K * C::N * C::M,
+  int rows = grid;
+  if (GA::DENSE) {
+    const int nch = contract_chunks<C>((long)BT);
+    const int chunk = (int)((BT + nch - 1) / nch);
+    float* crow = partials + (size_t)grid * psz;
+    cudaMemsetAsync(crow, 0, sizeof(float) * (size_t)nch * psz, s);   // C (shared) columns of these rows stay zero
+    constexpr int K = C::K;
+    k_mode_contract<K><<<dim3((C::N * C::N + 255) / 256, nch), 256, 0, s>>>(a.alpha, dn.A, (long)BT, C::N * C::N, chunk, crow, psz, GA::fA, 0, 0);
+    k_mode_contract<K><<<dim3((C::N * C::M + 255) / 256, nch), 256, 0, s>>>(a.alpha, dn.B, (long)BT, C::N * C::M, chunk, crow, psz, GA::fB, 0, 0);
+    if (C::QPM)
+      k_mode_contract<K><<<dim3((C::N * C::N + 255) / 256, nch), 256, 0, s>>>(a.alpha, dn.Q, (long)BT, C::N * C::N, chunk, crow, psz, GA::fQ, 0, 0);
+    if (!C::CSH)
+      k_mode_contract<K><<<dim3((C::N * C::P + 255) / 256, nch), 256, 0, s>>>(a.alpha, dn.Ct, (long)BT, C::N * C::P, chunk, crow, psz, GA::fC, C::P, C::N);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    rows += nch;
+  }
+  k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
                                               C::K * C::P * C::N, gp);
   return (int)cudaGetLastError();
 }

@@ -98,13 +98,28 @@ template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParam
   for (int b = 0; b < a.B; ++b) {
     GradAcc<C> acc;
     acc.zero();
-    std::vector<float> sacc(GradAcc<C>::PSZ, 0.f);
-    acc.sacc = sacc.data();
+    using GA = GradAcc<C>;
+    const size_t BTs = (size_t)a.B * a.T;
+    static std::vector<float> dA, dB, dQ, dCt;
+    dA.assign(BTs * C::N * C::N, 0.f); dB.assign(BTs * C::N * C::M, 0.f); dQ.assign(BTs * C::N * C::N, 0.f); dCt.assign(BTs * C::N * C::P, 0.f);
+    acc.dnA = dA.data(); acc.dnB = dB.data(); acc.dnQ = dQ.data(); acc.dnCt = dCt.data();
     acc.on = true;
     bwd_sweep3<C>(a, w, base.data(), tl, g, b, true, acc);
     bwd_sweep4<C>(a, w, base.data(), tl, g, b, true, acc);
-    if (GradAcc<C>::SM) { for (int i = 0; i < GradAcc<C>::PSZ; ++i) gp[i] += (double)sacc[i]; }
-    else acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
+    acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
+    if (GA::DENSE) {   // host version of k_mode_contract for this sequence's steps
+      for (int t = 0; t < a.T; ++t) {
+        const size_t bt = (size_t)b * a.T + t;
+        for (int k = 0; k < C::K; ++k) {
+          const double al = a.alpha[bt * C::K + k];
+          for (int e = 0; e < C::N * C::N; ++e) gp[GA::fA + k * C::N * C::N + e] += al * dA[bt * C::N * C::N + e];
+          for (int e = 0; e < C::N * C::M; ++e) gp[GA::fB + k * C::N * C::M + e] += al * dB[bt * C::N * C::M + e];
+          if (C::QPM) for (int e = 0; e < C::N * C::N; ++e) gp[GA::fQ + k * C::N * C::N + e] += al * dQ[bt * C::N * C::N + e];
+          if (!C::CSH) for (int i = 0; i < C::N; ++i) for (int q = 0; q < C::P; ++q)
+            gp[GA::fC + (k * C::P + q) * C::N + i] += al * dCt[bt * C::N * C::P + i * C::P + q];
+        }
+      }
+    }
   }
   if (dbg) {
     memcpy(dbg[0], wSf.data(), nn * 4); memcpy(dbg[1], wSp.data(), nn * 4);
