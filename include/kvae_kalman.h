@@ -39,8 +39,9 @@
 extern "C" {
 #endif
 
-#define KVAE_ABI_VERSION 2
+#define KVAE_ABI_VERSION 3
 #define KVAE_FLAG_SMOOTH_ONLY 1  /* kvae_dims.flags: forward entry skips the filter sweep (states given) */
+#define KVAE_FLAG_ELBO_ONLY 2    /* kvae_dims.flags: kvae_kf_bwd differentiates the ELBO alone, see kvae_grads */
 
 typedef struct kvae_dims {
   int32_t B;          /* sequences in this call (the per-rank shard)               */
@@ -130,6 +131,11 @@ typedef struct kvae_grads {
   float* dBm;     /* [K,n,m]                                              */
   float* dC;      /* [K,p,n]  (c_shared: only dC[0] is non-zero)          */
   float* dQ;      /* [K,n,n]  q_per_mode only; else may be NULL           */
+  /* KVAE_FLAG_ELBO_ONLY: gradient of g_elbo*elbo with (mus_smooth, Sigmas_smooth) treated as free inputs
+   * (KalmanFilter.elbo called with states that are not this library's own smoothed states): dmus/dSigmas
+   * receive d elbo / d mu, d elbo / d Sigma; dY, dU, dalpha, dA.. hold the ELBO's direct terms only. */
+  float* dmus;    /* [B,T,n]   */
+  float* dSigmas; /* [B,T,n,n] */
 } kvae_grads;
 
 /* Explicit adjoint (reverse-time) pass: gradient of

@@ -35,7 +35,7 @@ class KvaeCotangents(Structure):
 
 
 class KvaeGrads(Structure):
-    _fields_ = [(k, c_void_p) for k in ("dY", "dU", "dalpha", "dA", "dBm", "dC", "dQ")]
+    _fields_ = [(k, c_void_p) for k in ("dY", "dU", "dalpha", "dA", "dBm", "dC", "dQ", "dmus", "dSigmas")]
 
 
 class KvaeError(RuntimeError):
@@ -70,7 +70,7 @@ def lib():
     L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
                               c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads), c_void_p,
                               c_void_p, c_int, c_void_p]
-    if L.kvae_abi_version() != 2:
+    if L.kvae_abi_version() != 3:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
     return L
@@ -105,6 +105,7 @@ def _check(rc, what):
 
 
 FLAG_SMOOTH_ONLY = 1
+FLAG_ELBO_ONLY = 2
 
 
 def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0, flags=0):

@@ -19,8 +19,11 @@ struct BwdArgs {
   float *dY, *dU, *dalpha;          // dU nullable
   // scratch [B,T,...]
   float *w_Sig_f, *w_mu_f, *w_Sig_p, *w_mu_p;
+  float *e_dSig, *e_dmu;            // elbo_only outputs [B,T,N,N], [B,T,N]
   float c_elbo;                     // g_elbo / max(sum mask, 1); 0 = no ELBO term
   float jitter;
+  int elbo_only;                    // 1: adjoint of the ELBO alone w.r.t. (mu, Sigma) given as the smoothed states:
+                                    //    no smoother / filter adjoint; w_Sig_f / w_mu_f receive dSigma / dmu
 };
 
 // Per-warp tiles of the backward sweeps: 8 [n x n] + 3 [n x p] + 2 vector slots.
@@ -415,7 +418,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     load_rows_opt<R, N>(w.c_Sig_f, (bt * N + row0) * N, Sfb);
     load_vec_opt<R>(w.c_mu_f, bt * N + row0, mfb);
     float Ssb1[R][N], msb1[R];
-    if (has_next) {
+    if (has_next && !w.elbo_only) {
       const float (&Sf)[R][N] = cu.Sf;
       const float (&Sp1)[R][N] = cu.Sp1;
       const float (&Ss1)[R][N] = cu.Ss1;

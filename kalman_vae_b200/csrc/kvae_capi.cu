@@ -137,6 +137,7 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
   if (g_elbo && (!eps || !terms)) return fail(-1, "g_elbo given without eps/terms");
   if (!grads->dY || !grads->dalpha || !grads->dA || !grads->dBm || !grads->dC) return fail(-1, "null gradient buffer");
   if (dd.q_per_mode && !grads->dQ) return fail(-1, "dQ required when q_per_mode");
+  if ((dd.flags & KVAE_FLAG_ELBO_ONLY) && (!grads->dmus || !grads->dSigmas || !g_elbo)) return fail(-1, "ELBO_ONLY needs dmus, dSigmas and g_elbo");
   if (in->A_dense) return fail(-2, "explicit per-step matrices are supported by the forward entry only");
   DeviceGuard guard(device);
   kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace};

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   acc.on = active;
   acc.dnA = dn.A; acc.dnB = dn.B; acc.dnQ = dn.Q; acc.dnCt = dn.Ct;
   bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
-  bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
+  if (!w.elbo_only) bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
   cta_reduce_acc<C>(acc, g, active, tiles_all, partials + (size_t)blockIdx.x * GradAcc<C>::PSZ);
 }
 
@@ -344,6 +344,7 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   w.w_Sig_p = reinterpret_cast<float*>(p); p += nn;
   w.w_mu_f = reinterpret_cast<float*>(p); p += nv;
   w.w_mu_p = reinterpret_cast<float*>(p); p += nv;
+  if (w.elbo_only) { w.w_Sig_f = w.e_dSig; w.w_mu_f = w.e_dmu; }   // the scratch IS the requested output
   DensePtrs dn{nullptr, nullptr, nullptr, nullptr};
   if (GA::DENSE) {
     dn.A = reinterpret_cast<float*>(p); p += nn;

@@ -112,6 +112,8 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
   }
   w.dY = x.grads->dY; w.dU = x.grads->dU; w.dalpha = x.grads->dalpha;
   w.jitter = x.jitter;
+  w.elbo_only = (d.flags & KVAE_FLAG_ELBO_ONLY) ? 1 : 0;
+  w.e_dSig = x.grads->dSigmas; w.e_dmu = x.grads->dmus;
   GradPtrs gp{x.grads->dA, x.grads->dBm, x.grads->dC, x.grads->dQ};
   const bool sw = d.q_per_mode != 0;
 #define X(l)                                                                                             \

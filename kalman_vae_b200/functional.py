@@ -148,15 +148,19 @@ def elbo_terms(pb: Problem, st: States, eps, jitter=1e-6, Y=None, U=None):
 
 
 def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=None, cot=None, need_dU=True,
-            Y_elbo=None, U_elbo=None):
-    """Explicit adjoint.  Returns dict(dY,dU,dalpha,dA,dBm,dC,dQ[,dY_elbo,dU_elbo])."""
+            elbo_only=False):
+    """Explicit adjoint.  Returns dict(dY,dU,dalpha,dA,dBm,dC,dQ[,dmus,dSigmas])."""
     B, T, n, p, m, K = pb.shape
     dev = pb.Y.device
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     grads = dict(dY=e(B, T, p), dU=e(B, T, m) if need_dU else None, dalpha=e(B, T, K),
                  dA=e(K, n, n), dBm=e(K, n, m), dC=e(K, p, n), dQ=e(K, n, n) if pb.q_per_mode else None)
-    ws = workspace(dev, "bwd", capi.bwd_workspace_bytes(pb.dims))
-    capi.bwd(pb.dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
+    dims = pb.dims
+    if elbo_only:
+        grads["dmus"], grads["dSigmas"] = e(B, T, n), e(B, T, n, n)
+        dims = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.lanes, capi.FLAG_ELBO_ONLY)
+    ws = workspace(dev, "bwd", capi.bwd_workspace_bytes(dims))
+    capi.bwd(dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
     return grads
 
 
@@ -228,3 +232,32 @@ class FusedElboFunction(torch.autograd.Function):
         g_extra = (g * ctx.terms[6]).reshape(()) if ctx.has_extra else None
         return (None, None, None, None, g_extra, gr["dY"], gr["dU"] if ctx.has_U else None, gr["dalpha"], gr["dA"],
                 gr["dBm"], gr["dC"], gr["dQ"] if pb.q_per_mode else None)
+
+
+class ElboFunction(torch.autograd.Function):
+    """elbo(mu, Sigma, Y, U, alpha, A, Bm, C, Q) for ARBITRARY (mu, Sigma) tensors (e.g. filtered states, or
+    smoothed states of another call): the general form of KalmanFilter.elbo.  backward = ELBO adjoint only."""
+
+    @staticmethod
+    def forward(ctx, pb: Problem, eps, jitter, extra, mu, Sigma, Y, U, alpha, A, Bm, C, Q):
+        B, T, n, p, m, K = pb.shape
+        mu_c, Sig_c = prep(mu).reshape(B, T, n, 1), prep(Sigma)
+        st = States(mu_c, Sig_c, mu_c, Sig_c, mu_c, Sig_c)   # only the "smoothed" slots are read
+        terms = elbo_terms(pb, st, eps, jitter)
+        ctx.pb, ctx.st, ctx.eps, ctx.jitter, ctx.terms = pb, st, eps, jitter, terms
+        ctx.has_U, ctx.has_extra, ctx.mu_shape = U is not None, extra is not None, mu.shape
+        val = terms[5]
+        if extra is not None:
+            val = val + extra * terms[6]
+        return val.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        pb = ctx.pb
+        g = g.detach().to(torch.float32).reshape(1).contiguous()
+        gr = adjoint(pb, ctx.st, eps=ctx.eps, jitter=ctx.jitter, g_elbo=g, terms=ctx.terms, need_dU=ctx.has_U,
+                     elbo_only=True)
+        g_extra = (g * ctx.terms[6]).reshape(()) if ctx.has_extra else None
+        return (None, None, None, g_extra, gr["dmus"].reshape(ctx.mu_shape), gr["dSigmas"], gr["dY"],
+                gr["dU"] if ctx.has_U else None, gr["dalpha"], gr["dA"], gr["dBm"], gr["dC"],
+                gr["dQ"] if pb.q_per_mode else None)

@@ -8,9 +8,10 @@ caller can observe:
   * CUDA only.  There is no CPU implementation; a CPU tensor raises.
   * With shared emission (switching dynamics) `C_list` is the expanded view `C[0].expand(B,T,p,n)`
     instead of a materialised stack (same values).
-  * `elbo()` accepts the tensors returned by this object's own `filter()/smooth()` (it re-mixes
+  * `elbo()` needs `A_list/B_list/C_list` returned by this object's own `filter()/smooth()` (it re-mixes
     A_t/B_t/C_t/Q_t from alpha inside the kernel, so gradients reach alpha and the base matrices
-    directly); hand-made `A_list/B_list/C_list` tensors are not supported yet.
+    directly); `mu_t_T/Sigma_t_T`, `y_t`, `u_t`, `mask` may be arbitrary tensors.  With the smoothed states
+    of the same `smooth()` call the whole backward pass is one fused adjoint launch.
 """
 from __future__ import annotations
 
@@ -232,19 +233,16 @@ class KalmanFilter(nn.Module):
                 "filter()/smooth() (the kernels re-mix them from alpha); arbitrary list tensors are not supported yet")
         pb, st = prov.pb, prov.st
         B, T, n = pb.dims.B, pb.dims.T, pb.dims.n
-        same_states = (prov.smooth and prov.mus_smooth_ref() is mu_t_T and prov.Sigmas_smooth_ref() is Sigma_t_T)
-        if not same_states:
-            raise NotImplementedError(
-                "elbo(): mu_t_T/Sigma_t_T must be the smoothed states returned by the same smooth() call as the lists")
         if Q_list is not None:
             raise NotImplementedError("elbo(): explicit Q_list is not supported; Q is mixed from alpha in the kernel")
         mask_t = self._mask(mask, B, T, y_t)
-        if self.strict:   # value checks cost a host sync each; switch off with kf.strict = False
-            if (mask_t is None) != (pb.mask is None) or (mask_t is not None and mask_t.data_ptr() != pb.mask.data_ptr()
-                                                           and not torch.equal(mask_t.float(), pb.mask)):
-                raise NotImplementedError("elbo(): mask differs from the one given to smooth()")
-            if y_t.data_ptr() != pb.Y.data_ptr() and not torch.equal(y_t.detach().float(), pb.Y):
-                raise NotImplementedError("elbo(): y_t differs from the observations given to smooth()")
+        # fast path: the states are the smoothed states of the SAME smooth() call as the lists, on the same y/mask
+        fused = (prov.smooth and prov.mus_smooth_ref() is mu_t_T and prov.Sigmas_smooth_ref() is Sigma_t_T)
+        if fused and self.strict:   # value checks cost a host sync each; switch off with kf.strict = False
+            same_mask = (mask_t is None) == (pb.mask is None) and (
+                mask_t is None or mask_t.data_ptr() == pb.mask.data_ptr() or torch.equal(mask_t.float(), pb.mask))
+            same_y = y_t.data_ptr() == pb.Y.data_ptr() or torch.equal(y_t.detach().float(), pb.Y)
+            fused = same_mask and same_y
         eps = prep(self._draw_eps(B, T, n, y_t))
         dyn = self.dyn_params
         extra = None
@@ -252,16 +250,24 @@ class KalmanFilter(nn.Module):
             log_q, log_p = dyn.elbo_terms()                                        # :382-383
             extra = (log_p.sum() - log_q.sum()).to(torch.float32)
         Ys, Us, alpha, A, Bm, C, Q = prov.diff_inputs
-        # y_t / u_t of this call are the same values as smooth()'s inputs (checked above): route the
-        # gradient to the tensors the caller handed to elbo() AND smooth() by summing over both uses.
-        y_in = y_t if y_t.requires_grad or not (Ys is not None and Ys.requires_grad) else Ys
         dev = y_t.device
+        if fused:
+            # y_t / u_t of this call are the same values as smooth()'s inputs: route the gradient of BOTH uses
+            # (filter innovation and ELBO emission) to the tensor handed to elbo()
+            y_in = y_t if y_t.requires_grad or not (Ys is not None and Ys.requires_grad) else Ys
+            run = lambda jit: F.FusedElboFunction.apply(pb, st, eps, jit, extra, y_in, Us if Us is not None else None,
+                                                        alpha, A, Bm, C, Q)
+        else:
+            # general form: (mu, Sigma) are arbitrary tensors (filtered states, another call's smoothed states, ...)
+            u3 = u_t.squeeze(-1) if (u_t is not None and u_t.dim() == 4) else u_t
+            pb2 = Problem(prep(y_t), prep(u3), prep(mask_t), pb.alpha, pb.A, pb.Bm, pb.C, pb.Q, pb.R, pb.mu0, pb.Sigma0,
+                          pb.q_per_mode, pb.c_shared, lanes=self.lanes)
+            run = lambda jit: F.ElboFunction.apply(pb2, eps, jit, extra, mu_t_T, Sigma_t_T, y_t, u3, alpha, A, Bm, C, Q)
         jitter = 1e-6
         for attempt in range(5):                                                  # _safe_cholesky ladder (:291-296)
             if self.check_info:
                 F.info_word(dev).zero_()
-            val = F.FusedElboFunction.apply(pb, st, eps, jitter, extra, y_in, Us if Us is not None else None,
-                                            alpha, A, Bm, C, Q)
+            val = run(jitter)
             if not self.check_info or int(F.info_word(dev).item()) == 0:
                 break
             jitter *= 10.0      # a factorisation met a non-positive pivot: retry everything with 10x jitter

@@ -220,3 +220,35 @@ def test_safe_cholesky_matches_reference_ladder():
     S[1, 0, 0] = -1e-4          # needs a larger jitter than 1e-6
     L = kf._safe_cholesky(S)
     assert torch.isfinite(L).all() and torch.allclose(L[0], torch.linalg.cholesky(torch.eye(4, device=DEV) * (1 + 1e-3)), atol=1e-6)
+
+
+def test_elbo_general_form_with_filtered_states_and_lists_from_filter():
+    """kvae/kalman/test_filter.py usage: lists from filter(), states from a separate smooth() call; and the ELBO
+    of arbitrary (here: filtered) states.  Values and gradients w.r.t. mu/Sigma/y/alpha/A/C against the oracle."""
+    from oracle import kalman_oracle as ko
+    case, _, _, _ = load_golden("kalman_lstm")
+    kf, dyn = make_kf(case)
+    Y, U, mask = case["Y"].to(DEV), case["U"].to(DEV), case["mask"].to(DEV)
+    eps = case["eps"].to(DEV)
+    kf._draw_eps = lambda B, T, n, like: eps
+    with torch.no_grad():
+        mf, Sf, mp, Sp, A_list, B_list, C_list = kf.filter(Y, U, mask)
+    mu_in = mf.clone().requires_grad_(True)
+    Sig_in = Sf.clone().requires_grad_(True)
+    Yg = Y.clone().requires_grad_(True)
+    val = kf.elbo(mu_in, Sig_in, Yg, U, A_list, B_list, C_list, mask=mask)
+    gmu, gSig, gY, gal, gA, gC = torch.autograd.grad(val, [mu_in, Sig_in, Yg, dyn.alpha, dyn.A, dyn.C])
+    # oracle: same ELBO on the same (fp64) inputs with autograd
+    d = lambda k: case[k].double()
+    mu64 = mf.detach().cpu().double().requires_grad_(True)
+    Sg64 = Sf.detach().cpu().double().requires_grad_(True)
+    Y64 = d("Y").clone().requires_grad_(True)
+    al64, A64, C64 = d("alpha").clone().requires_grad_(True), d("A").clone().requires_grad_(True), d("C").clone().requires_grad_(True)
+    A_seq, B_seq, C_seq, Q_seq = ko.mix(al64, A64, d("B"), C64, d("Q"), False, False)
+    ref = ko.elbo(mu64, Sg64, Y64, d("U"), A_seq, B_seq, C_seq, Q_seq, d("R"), d("mu0"), d("Sigma0"), d("mask"), d("eps"))
+    rg = torch.autograd.grad(ref, [mu64, Sg64, Y64, al64, A64, C64])
+    rel = lambda a, b: float((a.detach().cpu().double() - b).norm() / b.norm())
+    assert rel(val, ref) < 2e-6
+    for name, got, want in zip(("dmu", "dSigma", "dY", "dalpha", "dA", "dC"), (gmu, gSig, gY, gal, gA, gC), rg):
+        want = want.reshape(got.shape) if name != "dSigma" else 0.5 * (want + want.mT)   # kernel returns the symmetric gradient
+        assert rel(got, want) < 2e-4, (name, rel(got, want))
