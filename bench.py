@@ -10,8 +10,10 @@ mask=1.  One step = smooth (filter+smoother) + elbo + backward (all gradients).
 
 One JSON line on stdout (rank 0):
   value      sequence-steps/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the public API (KalmanFilter.smooth/.elbo/.backward) with pinned HOST
-             buffers: H2D of the step's inputs and D2H of loss + parameter gradients inside the timed region
+  e2e        same metric with pinned HOST input buffers through engine.HostPipeline: every step copies its five
+             input tensors host->device (copy stream, overlapping the previous step) and its parameter gradients +
+             ELBO terms device->host inside the timed region
+  e2e_autograd  same through the reference-shaped calls KalmanFilter.smooth/.elbo/autograd.grad
   roofline   dominant kernel's algorithmic HBM bytes / its CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline  the CPU port of the reference algorithm (oracle/) timed on this box's host cores
 """
@@ -32,6 +34,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from kalman_vae_b200.synthetic import CONFIGS, Shape, make_case  # noqa: E402
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 from the committed `ncu --set full` capture
+# (profiles/, latest round); None = not captured
+NCU_TRAFFIC_BYTES = {"k_bwd": 53.8e6, "k_filter_smooth": 22.2e6}
 
 METRIC = "kalman_filter_smoother_fwd_bwd_sequence_steps_per_sec"
 UNIT = "sequence-steps/s"
@@ -249,28 +255,65 @@ def run_cuda(args, rank, local_rank, world):
         from kalman_vae_b200 import capi as _c
         for s in sets:   # un-graphed single calls for kernel timing
             s._only_fwd = lambda s=s: _c.filter_smooth_fwd(s.pb.dims, s._inputs, s._states, s.A_list, s.B_list, s.C_list, s.info, s.dev)
-            s._only_elbo = lambda s=s: _c.elbo_fwd(s.pb.dims, s._inputs, s._states, s.eps, s.jitter, s.terms, s.ws_elbo, s.info, s.dev)
-            s._only_bwd = lambda s=s: _c.bwd(s.pb.dims, s._inputs, s._states, s.eps, s.jitter, s.g_elbo, s.terms, None, s.grads,
+            s._only_bwd = lambda s=s: _c.bwd(s.dims_bwd, s._inputs, s._states, s.eps, s.jitter, s.g_elbo, s.terms, None, s.grads,
                                              s.ws_bwd, s.info, s.dev)
         kt["k_filter_smooth"] = time_call("_only_fwd")
-        kt["k_elbo(+final)"] = time_call("_only_elbo")
-        kt["k_bwd(+param_final)"] = time_call("_only_bwd")
+        kt["k_bwd(+bwd_final)"] = time_call("_only_bwd")
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end through the public API with pinned host buffers
+    # ---- end-to-end with pinned HOST inputs
+    #  (1) e2e: HostPipeline (engine.py) -- H2D of the five per-step input tensors on a copy stream (overlapping the
+    #      previous step's compute), the step graph, D2H of [parameter gradients | ELBO terms]; the host reads every
+    #      step's ELBO (one step late, as a trainer logging its loss would)
+    #  (2) e2e_autograd: the reference-shaped calls KalmanFilter.smooth -> .elbo -> torch.autograd.grad, same copies
     e2e = None
+    e2e_autograd = None
     if not args.no_e2e:
+        from kalman_vae_b200.engine import HostPipeline
         case = make_case(shape, seed=1234 + rank)
+        host = {k: case[k].pin_memory() for k in ("Y", "U", "mask", "alpha", "eps")}
+        params = {k: case[k].to(dev).contiguous() for k in ("A", "B", "C", "Q", "R", "mu0", "Sigma0")}
+        pipe = HostPipeline((shape.B, shape.T, shape.n, shape.p, shape.m, shape.K), params, shape.q_per_mode, shape.c_shared,
+                            lanes=lanes, device=dev)
+        cs = pipe.compute_stream
+
+        def pipe_steps(n):
+            prev, last_elbo = None, None
+            for _ in range(n):
+                k = pipe.step(host["Y"], host["U"], host["mask"], host["alpha"], host["eps"])
+                if prev is not None:
+                    last_elbo, _ = pipe.result(prev)
+                prev = k
+            return prev, last_elbo
+
+        prev, _ = pipe_steps(max(args.warmup, 10))
+        pipe.result(prev)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(cs)
+        pipe.copy_stream.wait_event(a)
+        prev, _ = pipe_steps(args.steps)
+        b.record(cs)
+        elbo_last, _ = pipe.result(prev)
+        barrier()
+        t2 = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t2) / args.steps
+        e2e = {"value": world * shape.B * shape.T / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
+               "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "ms_per_step": ms_e2e, "elbo_last_step": elbo_last,
+               "api": "engine.HostPipeline.step(Y,U,mask,alpha,eps pinned host tensors) + .result(): H2D on a copy stream "
+                      "overlapping the previous step, fwd+ELBO+bwd graph, D2H of parameter gradients + ELBO terms"}
+
         dyn = PrecomputedWeights(case["A"], case["B"], case["C"], case["Q"] if shape.q_per_mode else None,
                                  switching=shape.q_per_mode)
         kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, case["mu0"], case["Sigma0"], dyn, lanes=lanes).to(dev)
         kf.strict = False
         kf.check_info = False
-        host = {k: case[k].pin_memory() for k in ("Y", "U", "mask", "alpha", "eps")}
         h2d = sum(v.numel() * 4 for v in host.values())
         out_host = torch.empty(1 + sum(p.numel() for p in dyn.parameters()), pin_memory=True)
         d2h = out_host.numel() * 4
-        params = list(dyn.parameters())
+        params_l = list(dyn.parameters())
 
         def e2e_step():
             d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -279,35 +322,36 @@ def run_cuda(args, rank, local_rank, world):
             kf._draw_eps = lambda B, T, n, like: d["eps"]
             outs = kf.smooth(Y, d["U"], d["mask"])
             val = kf.elbo(outs[0], outs[1], Y, d["U"], outs[6], outs[7], outs[8], mask=d["mask"])
-            grads = torch.autograd.grad(val, [Y, dyn.alpha] + params)
+            grads = torch.autograd.grad(val, [Y, dyn.alpha] + params_l)
             if world > 1:
                 from kalman_vae_b200.dist import allreduce_param_grads
                 allreduce_param_grads(list(grads[2:]))
             flat = torch.cat([val.detach().reshape(1)] + [g.reshape(-1) for g in grads[2:]])
             out_host.copy_(flat, non_blocking=True)
 
-        for _ in range(max(args.warmup, 20)):   # lets the caching allocator reach its steady state
+        n_auto = min(args.steps, 500)
+        for _ in range(max(min(args.warmup, 20), 10)):   # lets the caching allocator reach its steady state
             e2e_step()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        for _ in range(args.steps):
+        for _ in range(n_auto):
             e2e_step()
         b.record(stream)
         barrier()
-        t2 = torch.tensor([a.elapsed_time(b)], device=dev)
+        t3 = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t2) / args.steps
-        e2e = {"value": world * shape.B * shape.T / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-               "api": "KalmanFilter.smooth -> .elbo -> autograd.grad (pinned host inputs, loss+param grads read back)"}
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms_auto = float(t3) / n_auto
+        e2e_autograd = {"value": world * shape.B * shape.T / (ms_auto * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_auto, "steps": n_auto,
+                        "api": "KalmanFilter.smooth -> .elbo -> autograd.grad (pinned host inputs, loss+param grads read back)"}
 
     if rank == 0:
         # dominant kernel
         dom = max(kt, key=kt.get)
-        dom_bytes = {"k_filter_smooth": ab["fwd"], "k_elbo(+final)": ab["elbo"] + 4 * (shape.n + shape.n ** 2),
-                     "k_bwd(+param_final)": ab["bwd"]}[dom] * shape.B * shape.T
+        # k_bwd evaluates the ELBO as well (fused): its algorithmic traffic is the adjoint's (eps is read once)
+        dom_bytes = {"k_filter_smooth": ab["fwd"], "k_bwd(+bwd_final)": ab["bwd"]}[dom] * shape.B * shape.T
         achieved = dom_bytes / kt[dom] / 1e9
         cpu_val, cpu_times = (None, [])
         cpu = None
@@ -326,12 +370,12 @@ def run_cuda(args, rank, local_rank, world):
                        "lanes_per_sequence": lanes_used, "cuda_graphs": not args.no_graphs,
                        "l2": f"{nsets} rotating buffer sets of {set_bytes / 2**20:.0f} MiB each (> 126 MB L2 in total)",
                        "sharding": "batch dimension, contiguous per rank; ONE all-reduce per step of a flat buffer [parameter gradients | 5 ELBO sums]"},
-            "e2e": e2e, "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
+            "e2e": e2e, "e2e_autograd": e2e_autograd, "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_bwd launch at this workload from the
                          # committed ncu --set full capture (profiles/r01d_ncu_full_summary_cfg2.csv); null for other kernels
-                         "traffic": 53.8e6 if dom.startswith("k_bwd") else None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom.split("(")[0]), "peak_source": peak_src,
                          "algorithmic_bytes_per_seq_step": ab, "kernel_seconds": kt,
                          "whole_step_frac": ab["total"] * world * shape.B * shape.T / (ms_step * 1e-3) / 1e9 / (peak * world)},
             "cpu_baseline": cpu, "clocks": clocks,

@@ -39,9 +39,11 @@
 extern "C" {
 #endif
 
-#define KVAE_ABI_VERSION 3
+#define KVAE_ABI_VERSION 4
 #define KVAE_FLAG_SMOOTH_ONLY 1  /* kvae_dims.flags: forward entry skips the filter sweep (states given) */
 #define KVAE_FLAG_ELBO_ONLY 2    /* kvae_dims.flags: kvae_kf_bwd differentiates the ELBO alone, see kvae_grads */
+#define KVAE_FLAG_WITH_ELBO 4    /* kvae_dims.flags: kvae_kf_bwd also EVALUATES the ELBO (fused value + adjoint), see below */
+#define KVAE_FLAG_RAW_SUMS 8     /* with KVAE_FLAG_WITH_ELBO: leave every gradient un-normalised (data-parallel callers) */
 
 typedef struct kvae_dims {
   int32_t B;          /* sequences in this call (the per-rank shard)               */
@@ -54,7 +56,7 @@ typedef struct kvae_dims {
                       /* 0: Q is [n,n] fixed (lstm, KalmanFilter.Q buffer)        */
   int32_t c_shared;   /* 1: C_t = C[0] (switching); 0: C_t = sum_k alpha_k C_k    */
   int32_t lanes;      /* lanes of a warp that own one sequence; 0 = library picks */
-  int32_t flags;      /* KVAE_FLAG_* (forward entry only)                         */
+  int32_t flags;      /* KVAE_FLAG_*                                              */
 } kvae_dims;
 
 /* problem inputs shared by all entry points */
@@ -146,7 +148,7 @@ typedef struct kvae_grads {
  * value).  `cot` may be NULL.  workspace: kvae_kf_bwd_workspace_bytes(d) bytes. */
 size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d);
 int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
-                const float* eps, float jitter, const float* g_elbo, const float* terms,
+                const float* eps, float jitter, const float* g_elbo, float* terms,
                 const kvae_cotangents* cot, const kvae_grads* grads, void* workspace,
                 int32_t* info, int device, void* stream);
 

@@ -70,7 +70,7 @@ def lib():
     L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
                               c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads), c_void_p,
                               c_void_p, c_int, c_void_p]
-    if L.kvae_abi_version() != 3:
+    if L.kvae_abi_version() != 4:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
     return L
@@ -106,6 +106,8 @@ def _check(rc, what):
 
 FLAG_SMOOTH_ONLY = 1
 FLAG_ELBO_ONLY = 2
+FLAG_WITH_ELBO = 4     # kvae_kf_bwd evaluates the ELBO too (writes terms) and normalises the gradients itself
+FLAG_RAW_SUMS = 8      # ... but leaves the 1/max(sum mask,1) factor to the caller (data parallel)
 
 
 def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0, flags=0):

@@ -20,8 +20,13 @@ struct BwdArgs {
   // scratch [B,T,...]
   float *w_Sig_f, *w_mu_f, *w_Sig_p, *w_mu_p;
   float *e_dSig, *e_dmu;            // elbo_only outputs [B,T,N,N], [B,T,N]
+  float *terms_out;                 // with_elbo: the 8 ELBO terms (see include/kvae_kalman.h) are written here
   float c_elbo;                     // g_elbo / max(sum mask, 1); 0 = no ELBO term
   float jitter;
+  int with_elbo;                    // 1: sweep 3 also accumulates the ELBO value sums (fused forward value: the
+                                    //    separate ELBO kernel is not needed; c_elbo then excludes the normaliser)
+  int raw_sums;                     // with_elbo: 1 = leave the gradients un-normalised (data parallel callers apply
+                                    //    the GLOBAL 1/max(sum mask,1) after their all-reduce)
   int elbo_only;                    // 1: adjoint of the ELBO alone w.r.t. (mu, Sigma) given as the smoothed states:
                                     //    no smoother / filter adjoint; w_Sig_f / w_mu_f receive dSigma / dmu
 };
@@ -205,7 +210,7 @@ template <class C> KV_FN void load_s3(const Args& a, long bt, bool has_next, boo
 // ---------------------------------------------------------------------------------------
 template <class C>
 KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const BTiles<C>& tl, const Group<C::L, C::R>& g,
-                      int b, bool active, GradAcc<C>& acc) {
+                      int b, bool active, GradAcc<C>& acc, double (&el)[5]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L, K = C::K;
   constexpr bool MEM = C::MEM;
   const TileRef T0 = tl.nn(0), T1 = tl.nn(1), T2 = tl.nn(2), T3 = tl.nn(3), T4 = tl.nn(4), T5 = tl.nn(5), TP = tl.nn(7);
@@ -297,6 +302,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     if (has_elbo) {
       float zbar_own[R];
       KV_UNROLL for (int r = 0; r < R; ++r) zbar_own[r] = xbar_own[r];
+      float v_tr = 0.f, v_em = 0.f, v_in = 0.f, v_en = 0.f;   // this lane's share of the ELBO value terms of step t
       if (has_next) {
         ok = elbo_sample_rows<C>(g, T0, VB, cu.Ss1, cu.ms1, w.jitter, cu.eps1, es1) && ok;
         // x_{t+1} = z_{t+1} - A1 z_t - B1 u_{t+1};  q = Qj^-1 x;  xbar = -c q
@@ -318,6 +324,12 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
           ok = chol_dist<L, R>(g, Qs, LQ, invdQ, dgQ) && ok;
           auto LQ_v = publish<MEM, L, R, N>(g, LQ, T2);
           solve_vec_l<N>(x, LQ_v, invdQ);
+          if (w.with_elbo) {   // log N(x; 0, Qj) = -1/2 (n log 2pi + |LQ^-1 x|^2) - sum log diag LQ   (own-lane log terms)
+            float q2 = 0.f, ld = 0.f;
+            KV_UNROLL for (int j = 0; j < N; ++j) q2 = fmaf(x[j], x[j], q2);
+            KV_UNROLL for (int r = 0; r < R; ++r) ld += logf(dgQ[r]);
+            v_tr = (g.lane == 0 ? -0.5f * (N * KV_LOG2PI + q2) : 0.f) - ld;
+          }
           solve_vec_lt<N>(x, LQ_v, invdQ);        // x := q
           // Qbar_{t+1} += c/2 (q q^T - Qj^-1)
           float Qi[R][N], q_own[R];
@@ -328,6 +340,11 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
             Qb[r][j] += 0.5f * c * (q_own[r] * x[j] - Qi[r][j]);
         } else {
           solve_vec_l<N>(x, LQc_v, ec.invdQ);
+          if (w.with_elbo && g.lane == 0) {
+            float q2 = 0.f;
+            KV_UNROLL for (int j = 0; j < N; ++j) q2 = fmaf(x[j], x[j], q2);
+            v_tr = -0.5f * (N * KV_LOG2PI + q2) - ec.logdetQ;
+          }
           solve_vec_lt<N>(x, LQc_v, ec.invdQ);
         }
         KV_UNROLL for (int j = 0; j < N; ++j) xbar[j] = -c * x[j];
@@ -359,6 +376,11 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
         KV_UNROLL for (int q = 0; q < P; ++q) e[q] = in.y[q] - e[q];
         RegView<P, P> LR_v{ec.LR};
         solve_vec_l<P>(e, LR_v, ec.invdR);
+        if (w.with_elbo && g.lane == 0) {
+          float q2 = 0.f;
+          KV_UNROLL for (int q = 0; q < P; ++q) q2 = fmaf(e[q], e[q], q2);
+          v_em = (-0.5f * (P * KV_LOG2PI + q2) - ec.logdetR) * in.m;
+        }
         solve_vec_lt<P>(e, LR_v, ec.invdR);       // R^-1 e
         KV_UNROLL for (int q = 0; q < P; ++q) { e[q] = -c * in.m * e[q]; dy[q] += e[q]; }   // ebar
         KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -378,9 +400,29 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
         float wv[N], w_own[R];
         KV_UNROLL for (int j = 0; j < N; ++j) wv[j] = es.z[j] - base[Base<C>::oMu0 + j];
         solve_vec_l<N>(wv, L0_v, invd0);
+        if (w.with_elbo) {
+          float q2 = 0.f, ld = 0.f;
+          KV_UNROLL for (int j = 0; j < N; ++j) q2 = fmaf(wv[j], wv[j], q2);
+          KV_UNROLL for (int r = 0; r < R; ++r) ld += logf(dg0[r]);
+          v_in = (g.lane == 0 ? -0.5f * (N * KV_LOG2PI + q2) : 0.f) - ld;
+        }
         solve_vec_lt<N>(wv, L0_v, invd0);
         pick_own<C>(g, wv, w_own);
         KV_UNROLL for (int r = 0; r < R; ++r) zbar_own[r] = fmaf(-c, w_own[r], zbar_own[r]);
+      }
+      if (w.with_elbo) {   // entropy of step t, then add this step's terms to the lane's fp64 sums
+        float ld = 0.f;
+        KV_UNROLL for (int r = 0; r < R; ++r) ld += logf(es.dg[r]);
+        if (g.lane == 0) {
+          float e2 = 0.f;
+          KV_UNROLL for (int j = 0; j < N; ++j) e2 = fmaf(eps_cur[j], eps_cur[j], e2);
+          v_en = 0.5f * e2 + 0.5f * N * KV_LOG2PI;
+        }
+        v_en += ld;
+        if (active) {
+          el[0] += (double)v_tr; el[1] += (double)v_em; el[2] += (double)v_in; el[3] += (double)v_en;
+          if (g.lane == 0) el[4] += (double)in.m;
+        }
       }
       // mu_s-bar += zbar ; Sigma_s-bar += sym(Ls^-T Phi Ls^-1), Phi = tril_strict(v eps^T) + diag((v.eps + c)/2), v = Ls^T zbar
       KV_UNROLL for (int r = 0; r < R; ++r) msb[r] += zbar_own[r];

@@ -128,7 +128,7 @@ size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d) {
 }
 
 int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
-                const float* g_elbo, const float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
+                const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
                 void* workspace, int32_t* info, int device, void* stream) {
   kvae_dims dd;
   if (int rc = check_common(d, in, st, &dd)) return rc;
@@ -139,6 +139,16 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
   if (dd.q_per_mode && !grads->dQ) return fail(-1, "dQ required when q_per_mode");
   if ((dd.flags & KVAE_FLAG_ELBO_ONLY) && (!grads->dmus || !grads->dSigmas || !g_elbo)) return fail(-1, "ELBO_ONLY needs dmus, dSigmas and g_elbo");
   if (in->A_dense) return fail(-2, "explicit per-step matrices are supported by the forward entry only");
+  if (dd.flags & KVAE_FLAG_WITH_ELBO) {
+    if (!g_elbo) return fail(-1, "WITH_ELBO needs g_elbo, eps and terms");
+    const bool any_cot = cot && (cot->mus_smooth || cot->Sigmas_smooth || cot->mus_filt || cot->Sigmas_filt || cot->mus_pred ||
+                                 cot->Sigmas_pred || cot->A_list || cot->B_list || cot->C_list);
+    if (any_cot) return fail(-2, "WITH_ELBO cannot be combined with dense cotangents (they must not be normalised)");
+    if ((dd.flags & KVAE_FLAG_ELBO_ONLY) && !(dd.flags & KVAE_FLAG_RAW_SUMS))
+      return fail(-2, "WITH_ELBO|ELBO_ONLY needs RAW_SUMS (dmus/dSigmas are not covered by the fused normalisation)");
+  } else if (dd.flags & KVAE_FLAG_RAW_SUMS) {
+    return fail(-2, "RAW_SUMS without WITH_ELBO");
+  }
   DeviceGuard guard(device);
   kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace};
 #define X(n_, p_, m_, k_)                                                                                   \

@@ -259,7 +259,8 @@ static __global__ void __launch_bounds__(256) k_mode_contract(const float* __res
 
 template <class C>
 __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
-                                                  const float* __restrict__ terms, float* __restrict__ partials, DensePtrs dn) {
+                                                  const float* __restrict__ terms, float* __restrict__ partials, DensePtrs dn,
+                                                  double* __restrict__ elbo_partials) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
@@ -270,29 +271,93 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   const bool active = b < a.B;
   if (!active) b = a.B - 1;
   const BTiles<C> tl = warp_tiles<BTiles<C>>(tiles_all, C::L);
-  w.c_elbo = g_elbo ? (*g_elbo) * terms[6] : 0.f;
+  w.c_elbo = g_elbo ? (*g_elbo) * (w.with_elbo ? 1.0f : terms[6]) : 0.f;
   GradAcc<C> acc;
   acc.zero();
   acc.on = active;
   acc.dnA = dn.A; acc.dnB = dn.B; acc.dnQ = dn.Q; acc.dnCt = dn.Ct;
-  bwd_sweep3<C>(a, w, base, tl, g, b, active, acc);
+  double el[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  bwd_sweep3<C>(a, w, base, tl, g, b, active, acc, el);
   if (!w.elbo_only) bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
+  if (w.with_elbo) {   // per-CTA partial sums of the ELBO value terms (fixed order -> deterministic)
+    __shared__ double red[TPB<C> / 32][5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double v = el[i];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      double v = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < TPB<C> / 32; ++wq) v += red[wq][threadIdx.x];
+      elbo_partials[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
+    }
+  }
   cta_reduce_acc<C>(acc, g, active, tiles_all, partials + (size_t)blockIdx.x * GradAcc<C>::PSZ);
 }
 
-// sums the per-CTA partials and scatters into dA | dB | dC | dQ: one warp per parameter element, lanes
-// stride over the CTAs, fp64 accumulation, fixed shuffle tree -> deterministic
-static __global__ void k_param_final(const float* __restrict__ partials, int nblocks, int psz, int nA, int nB, int nC,
-                                     GradPtrs gp) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+// Final kernel of the backward pass.
+//  * blocks [0, nparam_blocks): sum the per-CTA parameter-gradient partials and scatter into dA | dB | dC | dQ: one warp
+//    per parameter element, lanes stride over the CTAs, fp64 accumulation, fixed shuffle tree -> deterministic.
+//  * fused-ELBO mode (elbo_partials != nullptr): every block first re-derives the normaliser 1/max(sum mask,1) from
+//    the per-CTA ELBO partials (same fixed order in every block); block 0 also writes terms[8].  Unless `raw`, the
+//    parameter gradients are multiplied by the normaliser and the remaining blocks scale dY / dalpha / dU in place
+//    (the adjoint ran with c = g_elbo because the mask sum was not known yet; it is linear in c).
+struct ScaleJob { float* p[3]; long n[3]; };
+static __global__ void __launch_bounds__(128) k_bwd_final(const float* __restrict__ partials, int nblocks, int psz, int nA, int nB,
+                                                          int nC, GradPtrs gp, const double* __restrict__ elbo_partials,
+                                                          int n_elbo_partials, float* __restrict__ terms, int raw,
+                                                          int nparam_blocks, ScaleJob sj) {
+  __shared__ double tot[5];
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float scale = 1.f;
+  if (elbo_partials) {
+    const bool all5 = (blockIdx.x == 0);
+    for (int q = wp; q < 5; q += 4) {
+      if (q == 4 || all5) {
+        double v = 0.0;
+        for (int i = lane; i < n_elbo_partials; i += 32) v += elbo_partials[(size_t)i * 5 + q];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) tot[q] = v;
+      }
+    }
+    __syncthreads();
+    const double nrm = tot[4] < 1.0 ? 1.0 : tot[4];
+    if (all5 && threadIdx.x == 0) {
+      for (int j = 0; j < 5; ++j) terms[j] = (float)tot[j];
+      terms[5] = (float)((tot[0] + tot[1] + tot[2] + tot[3]) / nrm);
+      terms[6] = (float)(1.0 / nrm);
+      terms[7] = 0.f;
+    }
+    if (!raw) scale = (float)(1.0 / nrm);
+  }
+  if ((int)blockIdx.x >= nparam_blocks) {   // in-place scaling of the per-step gradients
+    if (scale == 1.f) return;
+    const long nthreads = (long)(gridDim.x - nparam_blocks) * blockDim.x;
+    const long tid = (long)(blockIdx.x - nparam_blocks) * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float* p = sj.p[j];
+      if (!p) continue;
+      const long n4 = sj.n[j] >> 2;
+      f4* p4 = reinterpret_cast<f4*>(p);
+      for (long i = tid; i < n4; i += nthreads) { f4 v = p4[i]; v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; p4[i] = v; }
+      for (long i = (n4 << 2) + tid; i < sj.n[j]; i += nthreads) p[i] *= scale;
+    }
+    return;
+  }
+  const int i = blockIdx.x * (blockDim.x >> 5) + wp;
   if (i >= psz) return;
   double v = 0.0;
   for (int blk = lane; blk < nblocks; blk += 32) v += (double)partials[(size_t)blk * psz + i];
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   if (lane != 0) return;
-  const float f = (float)v;
+  const float f = (float)v * scale;
   if (i < nA) gp.dA[i] = f;
   else if (i < nA + nB) gp.dB[i - nA] = f;
   else if (i < nA + nB + nC) gp.dC[i - nA - nB] = f;
@@ -320,7 +385,8 @@ template <class C> size_t bwd_ws_bytes(int B, int T) {
     dense = nn + align256(sizeof(float) * BT * C::N * C::M) + (C::QPM ? nn : 0) +
             (C::CSH ? 0 : align256(sizeof(float) * BT * C::N * C::P));
   }
-  return 2 * nn + 2 * nv + dense + align256(sizeof(float) * rows * GA::PSZ);
+  const size_t ep = align256(sizeof(double) * 5 * (size_t)((B + GPB - 1) / GPB));
+  return 2 * nn + 2 * nv + dense + ep + align256(sizeof(float) * rows * GA::PSZ);
 }
 
 template <class C>
@@ -352,11 +418,12 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
     if (C::QPM) { dn.Q = reinterpret_cast<float*>(p); p += nn; }
     if (!C::CSH) { dn.Ct = reinterpret_cast<float*>(p); p += align256(sizeof(float) * BT * C::N * C::P); }
   }
+  const int grid = (a.B + GPB - 1) / GPB;
+  double* elbo_partials = reinterpret_cast<double*>(p); p += align256(sizeof(double) * 5 * (size_t)grid);
   float* partials = reinterpret_cast<float*>(p);
   constexpr int psz = GA::PSZ;
-  const int grid = (a.B + GPB - 1) / GPB;
   constexpr int tpb = TPB<C>;
-  k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials, dn);
+  k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials, dn, elbo_partials);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   int rows = grid;
@@ -376,8 +443,21 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
     if (e != cudaSuccess) return (int)e;
     rows += nch;
   }
-  k_param_final<<<(psz + 3) / 4, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
-                                              C::K * C::P * C::N, gp);
+  const int nparam_blocks = (psz + 3) / 4;
+  ScaleJob sj{{nullptr, nullptr, nullptr}, {0, 0, 0}};
+  int scale_blocks = 0;
+  if (w.with_elbo && !w.raw_sums) {
+    sj.p[0] = w.dY; sj.n[0] = (long)BT * C::P;
+    sj.p[1] = w.dalpha; sj.n[1] = (long)BT * C::K;
+    sj.p[2] = w.dU; sj.n[2] = w.dU ? (long)BT * C::M : 0;
+    const long total4 = (sj.n[0] + sj.n[1] + sj.n[2]) / 4;
+    scale_blocks = (int)((total4 + 128 * 8 - 1) / (128 * 8));
+    if (scale_blocks < 1) scale_blocks = 1;
+    if (scale_blocks > 148 * 8) scale_blocks = 148 * 8;
+  }
+  k_bwd_final<<<nparam_blocks + scale_blocks, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
+                                                           C::K * C::P * C::N, gp, w.with_elbo ? elbo_partials : nullptr, grid,
+                                                           w.terms_out, w.raw_sums, nparam_blocks, sj);
   return (int)cudaGetLastError();
 }
 

@@ -7,7 +7,7 @@
 namespace kvae {
 
 struct BwdExtra {
-  const float* eps; float jitter; const float* g_elbo; const float* terms;
+  const float* eps; float jitter; const float* g_elbo; float* terms;
   const kvae_cotangents* cot; const kvae_grads* grads; void* workspace;
 };
 

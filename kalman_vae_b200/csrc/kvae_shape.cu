@@ -113,6 +113,9 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
   w.dY = x.grads->dY; w.dU = x.grads->dU; w.dalpha = x.grads->dalpha;
   w.jitter = x.jitter;
   w.elbo_only = (d.flags & KVAE_FLAG_ELBO_ONLY) ? 1 : 0;
+  w.with_elbo = (d.flags & KVAE_FLAG_WITH_ELBO) ? 1 : 0;
+  w.raw_sums = (d.flags & KVAE_FLAG_RAW_SUMS) ? 1 : 0;
+  w.terms_out = x.terms;
   w.e_dSig = x.grads->dSigmas; w.e_dmu = x.grads->dmus;
   GradPtrs gp{x.grads->dA, x.grads->dBm, x.grads->dC, x.grads->dQ};
   const bool sw = d.q_per_mode != 0;

@@ -1,8 +1,8 @@
 """KalmanStep — the hot path as one pre-planned unit of work per rank.
 
-One step = smooth (filter + RTS smoother) -> ELBO -> explicit adjoint, on this rank's shard of the
-batch, with every buffer (states, lists, gradients, workspaces) allocated once and the kernel
-sequence captured in CUDA graphs.
+One step = smooth (filter + RTS smoother) -> ELBO value + explicit adjoint (one fused launch,
+KVAE_FLAG_WITH_ELBO), on this rank's shard of the batch, with every buffer (states, lists, gradients,
+workspaces) allocated once and the kernel sequence captured in a CUDA graph.
 
 Data parallelism (one process per GPU, batch sharded): the adjoint is linear in the upstream factor
 c = g / max(sum(mask), 1), so every rank runs its forward + adjoint with the normaliser left out
@@ -50,13 +50,16 @@ class KalmanStep:
         self.g_elbo = torch.ones(1, dtype=torch.float32, device=dev)
         self.grads = dict(dY=e(B, T, p), dU=e(B, T, m) if need_dU else None, dalpha=e(B, T, K), dA=views[0],
                           dBm=views[1], dC=views[2], dQ=views[3] if pb.q_per_mode else None)
+        self.world = torch.distributed.get_world_size(group) if kdist._active(group) else 1
+        # fused value + adjoint launch; under data parallelism the normaliser is applied after the all-reduce
+        self.dims_bwd = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.dims.lanes,
+                                       capi.FLAG_WITH_ELBO | (capi.FLAG_RAW_SUMS if self.world > 1 else 0))
         self.ws_elbo = torch.empty(max(capi.elbo_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
-        self.ws_bwd = torch.empty(max(capi.bwd_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
+        self.ws_bwd = torch.empty(max(capi.bwd_workspace_bytes(self.dims_bwd), 16), dtype=torch.uint8, device=dev)
         self.info = info_word(dev)
         self._inputs = pb.inputs()
         self._states = self.st.c_struct()
-        self.kernel_launches_per_step = 5  # k_filter_smooth, k_elbo, k_elbo_final, k_bwd, k_param_final
-        self.world = torch.distributed.get_world_size(group) if kdist._active(group) else 1
+        self.kernel_launches_per_step = 3  # k_filter_smooth, k_bwd (ELBO value + adjoint), k_bwd_final
         self.graph_main = self.graph_post = None
         if use_graphs:
             self._capture()
@@ -65,12 +68,7 @@ class KalmanStep:
     def _compute(self):
         capi.filter_smooth_fwd(self.pb.dims, self._inputs, self._states, self.A_list, self.B_list, self.C_list,
                                self.info, self.dev)
-        capi.elbo_fwd(self.pb.dims, self._inputs, self._states, self.eps, self.jitter, self.terms, self.ws_elbo,
-                      self.info, self.dev)
-        if self.world > 1:
-            # leave the normaliser out of the adjoint: c = g_elbo * terms[6] = max(sum mask,1) / max(sum mask,1) = 1
-            torch.clamp(self.terms[4:5], min=1.0, out=self.g_elbo)
-        capi.bwd(self.pb.dims, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms, None,
+        capi.bwd(self.dims_bwd, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms, None,
                  self.grads, self.ws_bwd, self.info, self.dev)
 
     def _post(self):
@@ -120,3 +118,85 @@ class KalmanStep:
         """smooth only (the imputation path): one launch, no collective."""
         capi.filter_smooth_fwd(self.pb.dims, self._inputs, self._states, self.A_list, self.B_list, self.C_list,
                                self.info, self.dev)
+
+
+class HostPipeline:
+    """KalmanStep for inputs that live in (pinned) HOST memory: the end-to-end form of the training step.
+
+    `slots` device-side copies of the per-step inputs (Y, U, mask, alpha, eps) are kept, each with its own
+    KalmanStep (states, gradients, CUDA graph).  A copy stream uploads step i+1 while the compute stream runs
+    step i; the compute of consecutive steps stays strictly ordered (a trainer updates the parameters in
+    between), only the host->device transfer overlaps.  Per step the pipeline
+        1. waits until the slot's previous step no longer reads its inputs,
+        2. copies the five input tensors host->device (cudaMemcpyAsync from pinned memory, copy stream),
+        3. replays the step graph (k_filter_smooth, k_bwd with the fused ELBO value, k_bwd_final) on the compute
+           stream [+ the one all-reduce under data parallelism],
+        4. copies [dA | dB | dC | dQ | terms] (one flat buffer) device->host into a pinned result buffer.
+    dY / dalpha (the gradients that flow on to the encoder and the dynamics network) stay on the device.
+    """
+
+    def __init__(self, shape, params, q_per_mode=False, c_shared=False, has_U=True, has_mask=True, lanes=0, slots=2,
+                 device=None, group=None, jitter=1e-6):
+        B, T, n, p, m, K = shape
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.dev, self.slots = dev, slots
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        self.inputs, self.steps, self.out_host = [], [], []
+        self.ev_in = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_free = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_out = [torch.cuda.Event() for _ in range(slots)]
+        self._used = [False] * slots
+        with torch.cuda.stream(self.compute_stream):
+            for _ in range(slots):
+                d = dict(Y=e(B, T, p), U=e(B, T, m) if has_U else None, mask=e(B, T) if has_mask else None,
+                         alpha=e(B, T, K), eps=e(B, T, n))
+                for t in d.values():   # defined contents for the graph-capture warm-up run
+                    if t is not None:
+                        t.zero_()
+                if d["mask"] is not None:
+                    d["mask"].fill_(1.0)
+                d["alpha"].fill_(1.0 / K)
+                pb = Problem(d["Y"], d["U"], d["mask"], d["alpha"], params["A"], params["B"], params["C"], params["Q"],
+                             params["R"], params["mu0"], params["Sigma0"], q_per_mode, c_shared, lanes=lanes)
+                self.inputs.append(d)
+                self.steps.append(KalmanStep(pb, d["eps"], jitter=jitter, use_graphs=True, group=group, need_dU=False))
+                self.out_host.append(torch.empty(self.steps[-1].flat.numel(), dtype=torch.float32).pin_memory())
+        self.compute_stream.synchronize()
+        self.h2d_bytes_per_step = sum(t.numel() * 4 for t in self.inputs[0].values() if t is not None)
+        self.d2h_bytes_per_step = self.out_host[0].numel() * 4
+        self.i = 0
+
+    def step(self, Y, U, mask, alpha, eps):
+        """Enqueues one step on host tensors (pinned for a truly asynchronous copy).  Returns the slot index to
+        pass to `result()`; does not synchronise."""
+        k = self.i % self.slots
+        self.i += 1
+        d = self.inputs[k]
+        with torch.cuda.stream(self.copy_stream):
+            if self._used[k]:
+                self.copy_stream.wait_event(self.ev_free[k])
+            for name, src in (("Y", Y), ("U", U), ("mask", mask), ("alpha", alpha), ("eps", eps)):
+                if d[name] is not None:
+                    d[name].copy_(src, non_blocking=True)
+            self.ev_in[k].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.ev_in[k])
+            self.steps[k].step()
+            self.ev_free[k].record(self.compute_stream)
+            self.out_host[k].copy_(self.steps[k].flat, non_blocking=True)
+            self.ev_out[k].record(self.compute_stream)
+        self._used[k] = True
+        return k
+
+    def result(self, k):
+        """Blocks until step `k`'s results are in host memory.  Returns (elbo, flat_host) where flat_host is the pinned
+        buffer [dA | dB | dC | dQ | pad | terms(8)] of that slot (valid until the slot is used again)."""
+        self.ev_out[k].synchronize()
+        out = self.out_host[k]
+        return float(out[out.numel() - 3]), out   # terms[5]
+
+    def device_grads(self, k):
+        """dY, dalpha (+ parameter-gradient views) of slot k on the device, ordered on the compute stream."""
+        return self.steps[k].grads

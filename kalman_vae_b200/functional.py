@@ -148,8 +148,9 @@ def elbo_terms(pb: Problem, st: States, eps, jitter=1e-6, Y=None, U=None):
 
 
 def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=None, cot=None, need_dU=True,
-            elbo_only=False):
-    """Explicit adjoint.  Returns dict(dY,dU,dalpha,dA,dBm,dC,dQ[,dmus,dSigmas])."""
+            elbo_only=False, with_elbo=False):
+    """Explicit adjoint.  Returns dict(dY,dU,dalpha,dA,dBm,dC,dQ[,dmus,dSigmas]).
+    with_elbo: fused value + adjoint (KVAE_FLAG_WITH_ELBO): `terms` is WRITTEN by the launch."""
     B, T, n, p, m, K = pb.shape
     dev = pb.Y.device
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -159,9 +160,22 @@ def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=N
     if elbo_only:
         grads["dmus"], grads["dSigmas"] = e(B, T, n), e(B, T, n, n)
         dims = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.lanes, capi.FLAG_ELBO_ONLY)
+    if with_elbo:
+        dims = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.lanes, capi.FLAG_WITH_ELBO)
     ws = workspace(dev, "bwd", capi.bwd_workspace_bytes(dims))
     capi.bwd(dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
     return grads
+
+
+_ones_cache = {}
+
+
+def _one(device):
+    w = _ones_cache.get(device)
+    if w is None:
+        w = torch.ones(1, dtype=torch.float32, device=device)
+        _ones_cache[device] = w
+    return w
 
 
 _COT_ORDER = ("mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
@@ -214,9 +228,17 @@ class FusedElboFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pb: Problem, st: States, eps, jitter, extra, Y, U, alpha, A, Bm, C, Q):
-        terms = elbo_terms(pb, st, eps, jitter)
-        ctx.pb, ctx.st, ctx.eps, ctx.jitter, ctx.terms = pb, st, eps, jitter, terms
         ctx.has_U = U is not None
+        ctx.eager = None
+        if any(ctx.needs_input_grad[5:]):
+            # a gradient will be asked for: evaluate the ELBO and its complete adjoint in ONE launch now
+            # (the adjoint recomputes every quantity of the ELBO anyway); backward() only scales by the upstream factor
+            terms = torch.empty(8, dtype=torch.float32, device=pb.Y.device)
+            ctx.eager = adjoint(pb, st, eps=eps, jitter=jitter, g_elbo=_one(pb.Y.device), terms=terms, need_dU=ctx.has_U,
+                                with_elbo=True)
+        else:
+            terms = elbo_terms(pb, st, eps, jitter)
+        ctx.pb, ctx.st, ctx.eps, ctx.jitter, ctx.terms = pb, st, eps, jitter, terms
         # extra: optional 0-dim tensor added inside the normalisation: (log_p - log_q).sum()
         val = terms[5]
         if extra is not None:
@@ -228,7 +250,11 @@ class FusedElboFunction(torch.autograd.Function):
     def backward(ctx, g):
         pb = ctx.pb
         g = g.detach().to(torch.float32).reshape(1).contiguous()
-        gr = adjoint(pb, ctx.st, eps=ctx.eps, jitter=ctx.jitter, g_elbo=g, terms=ctx.terms, need_dU=ctx.has_U)
+        if ctx.eager is not None:
+            names = ["dY", "dalpha", "dA", "dBm", "dC"] + (["dU"] if ctx.has_U else []) + (["dQ"] if pb.q_per_mode else [])
+            gr = dict(zip(names, torch._foreach_mul([ctx.eager[k] for k in names], g.reshape(()))))
+        else:
+            gr = adjoint(pb, ctx.st, eps=ctx.eps, jitter=ctx.jitter, g_elbo=g, terms=ctx.terms, need_dU=ctx.has_U)
         g_extra = (g * ctx.terms[6]).reshape(()) if ctx.has_extra else None
         return (None, None, None, None, g_extra, gr["dY"], gr["dU"] if ctx.has_U else None, gr["dalpha"], gr["dA"],
                 gr["dBm"], gr["dC"], gr["dQ"] if pb.q_per_mode else None)

@@ -79,7 +79,7 @@ COT_NAMES = ["mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred
              "A_list", "B_list", "C_list"]
 
 
-def bwd(case, states, g_elbo=1.0, cot=None, force_mem=False, jitter=1e-6):
+def bwd(case, states, g_elbo=1.0, cot=None, force_mem=False, jitter=1e-6, with_elbo=False):
     """states: the six state tensors (fp32). Returns dY,dU,dalpha,dA,dB,dC[,dQ]."""
     Y, U, mask, alpha, eps = (_f(case, k) for k in ("Y", "U", "mask", "alpha", "eps"))
     A, Bm, C, Q, R, mu0, S0 = (_f(case, k) for k in ("A", "B", "C", "Q", "R", "mu0", "Sigma0"))
@@ -96,16 +96,21 @@ def bwd(case, states, g_elbo=1.0, cot=None, force_mem=False, jitter=1e-6):
     info = torch.zeros(1, dtype=torch.int32)
     dbg = [torch.zeros(B, T, n, n), torch.zeros(B, T, n, n), torch.zeros(B, T, n), torch.zeros(B, T, n)]
     dbg_arr = (ctypes.c_void_p * 4)(*[d.data_ptr() for d in dbg])
+    el5 = (ctypes.c_double * 5)()
     rc = lib().hostsim_bwd(n, p, m, K, sw, int(force_mem), B, T, _p(Y), _p(U), _p(mask), _p(alpha), _p(eps),
                            _p(A), _p(Bm), _p(C), _p(Q), _p(R), _p(mu0), _p(S0),
                            _p(st["mus_filt"]), _p(st["Sigmas_filt"]), _p(st["mus_pred"]), _p(st["Sigmas_pred"]),
                            _p(st["mus_smooth"]), _p(st["Sigmas_smooth"]),
                            ctypes.c_float(c_elbo), ctypes.c_float(jitter), cot_arr,
-                           _p(dY), _p(dU), _p(dal), gp, _p(info), dbg_arr)
+                           _p(dY), _p(dU), _p(dal), gp, _p(info), dbg_arr, el5 if with_elbo else None)
     assert rc == 0
     flat = torch.tensor(list(gp), dtype=torch.float64)
     o = 0
     out = dict(dY=dY, dU=dU, dalpha=dal, info=int(info))
+    if with_elbo:   # the ELBO value accumulated by the adjoint sweep itself (fused value + adjoint mode)
+        e = list(el5)
+        out["elbo_terms"] = e
+        out["elbo"] = (e[0] + e[1] + e[2] + e[3]) / max(e[4], 1.0)
     out['_dbg'] = dict(Sf_b=dbg[0], Sp_b=dbg[1], mf_b=dbg[2], mp_b=dbg[3])
     for name, shp in (("dA", (K, n, n)), ("dB", (K, n, m)), ("dC", (K, p, n))) + ((("dQ", (K, n, n)),) if sw else ()):
         sz = shp[0] * shp[1] * shp[2]

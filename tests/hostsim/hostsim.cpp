@@ -85,7 +85,7 @@ extern "C" int hostsim_elbo(int N, int P, int M, int K, int switching, int force
   return -1;
 }
 
-template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParams& hp, double* gp, float** dbg) {
+template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParams& hp, double* gp, float** dbg, double* el5) {
   std::vector<float> base(Base<C>::total);
   for (int i = 0; i < Base<C>::total; ++i) base_fill<C>(base.data(), i, hp.A, hp.Bm, hp.C, hp.Q, hp.R, hp.mu0, hp.S0);
   std::vector<float> tiles(BTiles<C>::warp_total + 4);
@@ -104,7 +104,9 @@ template <class C> static void run_bwd(const Args& a, BwdArgs w, const HostParam
     dA.assign(BTs * C::N * C::N, 0.f); dB.assign(BTs * C::N * C::M, 0.f); dQ.assign(BTs * C::N * C::N, 0.f); dCt.assign(BTs * C::N * C::P, 0.f);
     acc.dnA = dA.data(); acc.dnB = dB.data(); acc.dnQ = dQ.data(); acc.dnCt = dCt.data();
     acc.on = true;
-    bwd_sweep3<C>(a, w, base.data(), tl, g, b, true, acc);
+    double el[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    bwd_sweep3<C>(a, w, base.data(), tl, g, b, true, acc, el);
+    if (el5) for (int i = 0; i < 5; ++i) el5[i] += el[i];
     bwd_sweep4<C>(a, w, base.data(), tl, g, b, true, acc);
     acc.for_each(0, [&](int idx, float v) { gp[idx] += (double)v; });
     if (GA::DENSE) {   // host version of k_mode_contract for this sequence's steps
@@ -133,7 +135,7 @@ extern "C" int hostsim_bwd(int N, int P, int M, int K, int switching, int force_
                            const float* mu0, const float* S0,
                            float* mu_f, float* Sig_f, float* mu_p, float* Sig_p, float* mu_s, float* Sig_s,
                            float c_elbo, float jitter, const float** cot9,
-                           float* dY, float* dU, float* dalpha, double* gparams, int* info, float** dbg) {
+                           float* dY, float* dU, float* dalpha, double* gparams, int* info, float** dbg, double* el5) {
   Args a{};
   a.B = B; a.T = T; a.Y = Y; a.U = U; a.mask = mask; a.alpha = alpha; a.eps = eps;
   a.mu_f = mu_f; a.Sig_f = Sig_f; a.mu_p = mu_p; a.Sig_p = Sig_p; a.mu_s = mu_s; a.Sig_s = Sig_s; a.info = info;
@@ -141,13 +143,15 @@ extern "C" int hostsim_bwd(int N, int P, int M, int K, int switching, int force_
   w.c_mu_s = cot9[0]; w.c_Sig_s = cot9[1]; w.c_mu_f = cot9[2]; w.c_Sig_f = cot9[3]; w.c_mu_p = cot9[4]; w.c_Sig_p = cot9[5];
   w.c_A = cot9[6]; w.c_B = cot9[7]; w.c_C = cot9[8];
   w.dY = dY; w.dU = dU; w.dalpha = dalpha; w.c_elbo = c_elbo; w.jitter = jitter;
+  w.with_elbo = el5 ? 1 : 0;
+  if (el5) for (int i = 0; i < 5; ++i) el5[i] = 0.0;
   HostParams hp{A, Bm, C, Q, R, mu0, S0};
 #define X(n, p, m, k)                                                                                   \
   if (N == n && P == p && M == m && K == k) {                                                           \
-    if (switching) { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, true, true, true>>(a, w, hp, gparams, dbg);      \
-                     else run_bwd<Cfg<n, p, m, k, 1, true, true, false>>(a, w, hp, gparams, dbg); }             \
-    else { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, false, false, true>>(a, w, hp, gparams, dbg);              \
-           else run_bwd<Cfg<n, p, m, k, 1, false, false, false>>(a, w, hp, gparams, dbg); }                     \
+    if (switching) { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, true, true, true>>(a, w, hp, gparams, dbg, el5);      \
+                     else run_bwd<Cfg<n, p, m, k, 1, true, true, false>>(a, w, hp, gparams, dbg, el5); }             \
+    else { if (force_mem) run_bwd<Cfg<n, p, m, k, 1, false, false, true>>(a, w, hp, gparams, dbg, el5);              \
+           else run_bwd<Cfg<n, p, m, k, 1, false, false, false>>(a, w, hp, gparams, dbg, el5); }                     \
     return 0;                                                                                           \
   }
   KVAE_FOR_EACH_SHAPE(X)

@@ -56,6 +56,18 @@ def test_forward_elbo_backward_match_reference(name, lanes):
     for k in GRAD_NAMES:
         if k in r32:
             check_close(f"{name}.L{lanes}.{k}", gr[k], r32[k], r64[k])
+    if "elbo" in r32:
+        # fused value + adjoint launch (KVAE_FLAG_WITH_ELBO): the ELBO against the reference, and the ELBO-only gradients
+        # against the two-call sequence (the goldens' gradients include the dense cotangents, which the fused mode excludes)
+        t_f = torch.empty(8, device=dev)
+        fused = F.adjoint(pb, st, eps=g["eps"], g_elbo=gel, terms=t_f, with_elbo=True)
+        plain = F.adjoint(pb, st, eps=g["eps"], g_elbo=gel, terms=terms)
+        torch.cuda.synchronize()
+        check_close(f"{name}.L{lanes}.elbo_fused", t_f[5], r32["elbo"], r64["elbo"])
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+        for k in ("dY", "dU", "dalpha", "dA", "dBm", "dC", "dQ"):
+            if fused[k] is not None:
+                assert rel(fused[k], plain[k]) < 5e-5, (name, lanes, k)   # fp32 noise floor of the cancelling sums
 
 
 @pytest.mark.parametrize("lanes", [1, 2, 4])

@@ -50,3 +50,21 @@ def test_adjoint_matches_reference_autograd(name, force_mem):
     for k in GRAD_NAMES:
         if k in r32:
             check_close(f"{name}.{k}", got[k], r32[k], r64[k])
+
+
+@pytest.mark.parametrize("force_mem", [False, True])
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_switch", "kalman_fractional", "kalman_rocket", "kalman_n8"])
+def test_fused_elbo_value_in_adjoint_sweep(name, force_mem):
+    """KVAE_FLAG_WITH_ELBO: the adjoint sweep accumulates the ELBO value itself; it must equal the ELBO kernel's
+    sums term by term and the reference's value, and leave the gradients unchanged."""
+    case, cot, r32, r64 = load_golden(name)
+    sep = driver.elbo(case, r32, force_mem=force_mem)
+    got = driver.bwd(case, r32, 1.0, None, force_mem=force_mem, with_elbo=True)
+    plain = driver.bwd(case, r32, 1.0, None, force_mem=force_mem)
+    assert got["info"] == 0
+    for i, k in enumerate(("trans", "emiss", "init", "entropy")):
+        assert abs(got["elbo_terms"][i] - sep[k]) <= 2e-6 * max(1.0, abs(sep[k])), (k, got["elbo_terms"][i], sep[k])
+    assert abs(got["elbo_terms"][4] - float(case["mask"].double().sum())) <= 1e-9 * case["mask"].numel()
+    check_close(name + ".elbo", torch.tensor(got["elbo"]), r32["elbo"], r64["elbo"])
+    for k in ("dY", "dalpha"):
+        assert torch.equal(got[k], plain[k])
