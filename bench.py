@@ -37,7 +37,7 @@ from kalman_vae_b200.synthetic import CONFIGS, Shape, make_case  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 from the committed `ncu --set full` capture
 # (profiles/, latest round); None = not captured
-NCU_TRAFFIC_BYTES = {"k_bwd": 53.8e6, "k_filter_smooth": 22.2e6}
+NCU_TRAFFIC_BYTES = {"k_bwd": 56.0e6, "k_filter_smooth": 20.7e6}   # profiles/r01e_ncu_full_summary_cfg2.csv
 
 METRIC = "kalman_filter_smoother_fwd_bwd_sequence_steps_per_sec"
 UNIT = "sequence-steps/s"
@@ -369,8 +369,10 @@ def run_cuda(args, rank, local_rank, world):
                                    f"K={shape.K}; smooth+elbo forward and explicit-adjoint backward",
                        "lanes_per_sequence": lanes_used, "cuda_graphs": not args.no_graphs,
                        "l2": f"{nsets} rotating buffer sets of {set_bytes / 2**20:.0f} MiB each (> 126 MB L2 in total)",
-                       "sharding": "batch dimension, contiguous per rank; ONE all-reduce per step of a flat buffer [parameter gradients | 5 ELBO sums]"},
-            "e2e": e2e, "e2e_autograd": e2e_autograd, "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
+                       "sharding": "batch dimension, contiguous per rank; ONE exchange per step of a flat buffer [parameter gradients | 5 ELBO sums]",
+                       "collective": sets[0].collective},
+            "e2e": e2e, "e2e_autograd": e2e_autograd,
+            "gpu_launches": (sets[0].kernel_launches_per_step + (2 if sets[0].peer is not None else 0)) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_bwd launch at this workload from the

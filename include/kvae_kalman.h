@@ -152,6 +152,31 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
                 const kvae_cotangents* cot, const kvae_grads* grads, void* workspace,
                 int32_t* info, int device, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Data parallelism (one process per GPU, batch sharded): the single exchange of the training step, i.e. the
+ * sum over ranks of [dA | dB | dC | dQ | 5 ELBO sums] and the GLOBAL normalisation 1/max(sum mask, 1)
+ * (kalman_filter.py:392-400), done by this library's own kernels over NVLink peer memory (CUDA IPC) instead of
+ * an NCCL all-reduce followed by scaling kernels.  The reference has no multi-device path.
+ *
+ *   kvae_dp_create   allocates this rank's exchange buffer on `device` and returns its IPC handle
+ *                    (kvae_dp_handle_bytes() bytes) for the caller to all-gather (any transport);
+ *                    nfloats = K*n*n + K*n*m + K*p*n (+ K*n*n if q_per_mode).
+ *   kvae_dp_connect  maps the peers' buffers; `handles` = world handles in rank order.
+ *   kvae_dp_finalize call after kvae_kf_bwd(KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS) on the same stream, on EVERY rank
+ *                    the same number of times: afterwards grads->dA/dBm/dC/dQ hold the normalised GLOBAL parameter
+ *                    gradients (bit-identical on all ranks: rank-ordered fp64 sums), terms[0..7] the global ELBO
+ *                    terms, and this rank's dY/dalpha/dU are scaled by the global normaliser.  Two launches, no host
+ *                    synchronisation, capturable in a CUDA graph.  info is set to 2 if a peer never arrives (~20 s).
+ */
+typedef struct kvae_dp_comm kvae_dp_comm;
+const char* kvae_dp_last_error(void);
+size_t kvae_dp_handle_bytes(void);
+int kvae_dp_create(int device, int rank, int world, size_t nfloats, kvae_dp_comm** out, void* handle_out);
+int kvae_dp_connect(kvae_dp_comm* c, const void* handles);
+int kvae_dp_destroy(kvae_dp_comm* c);
+int kvae_dp_finalize(const kvae_dims* d, kvae_dp_comm* c, const kvae_grads* g, float* terms, int32_t* info,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

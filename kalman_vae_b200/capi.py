@@ -70,6 +70,12 @@ def lib():
     L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
                               c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads), c_void_p,
                               c_void_p, c_int, c_void_p]
+    L.kvae_dp_last_error.restype = c_char_p
+    L.kvae_dp_handle_bytes.restype = c_size_t
+    L.kvae_dp_create.argtypes = [c_int, c_int, c_int, c_size_t, POINTER(c_void_p), c_void_p]
+    L.kvae_dp_connect.argtypes = [c_void_p, c_void_p]
+    L.kvae_dp_destroy.argtypes = [c_void_p]
+    L.kvae_dp_finalize.argtypes = [POINTER(KvaeDims), c_void_p, POINTER(KvaeGrads), c_void_p, c_void_p, c_void_p]
     if L.kvae_abi_version() != 4:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
@@ -80,6 +86,7 @@ EXPORTED_SYMBOLS = [
     "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
     "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
+    "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize",
 ]
 
 
@@ -170,3 +177,36 @@ def bwd(dims, inputs, states, eps, jitter, g_elbo, terms, cot, grads, workspace,
                            _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(cot_s), byref(grads_s),
                            c_void_p(workspace.data_ptr()), _ptr(info, "info"), device.index, _stream(device))
     _check(rc, "kvae_kf_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# data-parallel exchange over NVLink peer memory (kvae_dp_*)
+# ---------------------------------------------------------------------------------------------------------
+def _check_dp(rc, what):
+    if rc != 0:
+        raise KvaeError(f"{what} failed (status {rc}): {lib().kvae_dp_last_error().decode()}")
+
+
+def dp_create(device, rank, world, nfloats):
+    """-> (comm handle (c_void_p), IPC handle bytes to all-gather)"""
+    L = lib()
+    comm = c_void_p()
+    buf = ctypes.create_string_buffer(int(L.kvae_dp_handle_bytes()))
+    _check_dp(L.kvae_dp_create(device.index, rank, world, nfloats, byref(comm), buf), "kvae_dp_create")
+    return comm, buf.raw
+
+
+def dp_connect(comm, handles):
+    blob = b"".join(handles)
+    _check_dp(lib().kvae_dp_connect(comm, ctypes.c_char_p(blob)), "kvae_dp_connect")
+
+
+def dp_destroy(comm):
+    if comm:
+        lib().kvae_dp_destroy(comm)
+
+
+def dp_finalize(dims, comm, grads, terms, info, device):
+    grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
+    rc = lib().kvae_dp_finalize(byref(dims), comm, byref(grads_s), _ptr(terms, "terms"), _ptr(info, "info"), _stream(device))
+    _check_dp(rc, "kvae_dp_finalize")

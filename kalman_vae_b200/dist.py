@@ -60,3 +60,34 @@ def allreduce_param_grads(grads, group=None):
         g.copy_(flat[o:o + n].view_as(g))
         o += n
     return grads
+
+
+class PeerExchange:
+    """The data-parallel exchange of the step over NVLink peer memory (csrc/kvae_dp.cu): every rank exports a small
+    cudaMalloc'ed exchange buffer through CUDA IPC, the handles are all-gathered ONCE with torch.distributed, and from
+    then on kvae_dp_finalize sums [parameter gradients | ELBO sums] over the ranks, applies the global normaliser and
+    scales the local per-step gradients in its own kernels: no NCCL call on the hot path."""
+
+    def __init__(self, device, nfloats, group=None):
+        from . import capi
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm, handle = capi.dp_create(device, self.rank, self.world, nfloats)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        ok, err = 1, ""
+        try:
+            capi.dp_connect(self.comm, handles)
+        except capi.KvaeError as e:   # e.g. no peer access between the devices
+            ok, err = 0, str(e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, (ok, err), group=group)
+        if not all(o for o, _ in oks):
+            capi.dp_destroy(self.comm)
+            self.comm = None
+            raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(e for o, e in oks if not o))
+
+    def close(self):
+        from . import capi
+        if self.comm is not None:
+            capi.dp_destroy(self.comm)
+            self.comm = None

@@ -17,6 +17,8 @@ launches exactly the same kernels.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import capi
@@ -60,6 +62,19 @@ class KalmanStep:
         self._inputs = pb.inputs()
         self._states = self.st.c_struct()
         self.kernel_launches_per_step = 3  # k_filter_smooth, k_bwd (ELBO value + adjoint), k_bwd_final
+        # data parallel: the exchange runs in this library's own kernels over NVLink peer memory (dist.PeerExchange);
+        # KVAE_DP_COLLECTIVE=nccl selects the torch.distributed all-reduce + scaling kernels instead
+        self.peer = None
+        self.collective = "none"
+        if self.world > 1:
+            self.collective = "nccl"
+            if os.environ.get("KVAE_DP_COLLECTIVE", "peer") == "peer":
+                try:
+                    self.peer = kdist.PeerExchange(dev, psz, group)
+                    self.collective = "nvlink-peer-memory"
+                except RuntimeError as err:
+                    import warnings
+                    warnings.warn(f"{err}; using the NCCL all-reduce")
         self.graph_main = self.graph_post = None
         if use_graphs:
             self._capture()
@@ -70,6 +85,8 @@ class KalmanStep:
                                self.info, self.dev)
         capi.bwd(self.dims_bwd, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms, None,
                  self.grads, self.ws_bwd, self.info, self.dev)
+        if self.peer is not None:
+            capi.dp_finalize(self.pb.dims, self.peer.comm, self.grads, self.terms, self.info, self.dev)
 
     def _post(self):
         """after the all-reduce: apply the GLOBAL normaliser"""
@@ -88,14 +105,14 @@ class KalmanStep:
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):   # warm-up outside capture (sets kernel attributes, loads modules)
             self._compute()
-            if self.world > 1:
+            if self.world > 1 and self.peer is None:
                 self._post()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.graph_main = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_main):
             self._compute()
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             self.graph_post = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_post):
                 self._post()
@@ -106,7 +123,7 @@ class KalmanStep:
             self.graph_main.replay()
         else:
             self._compute()
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             torch.distributed.all_reduce(self.flat[:self.n_reduce], op=torch.distributed.ReduceOp.SUM, group=self.group)
             if self.graph_post is not None:
                 self.graph_post.replay()

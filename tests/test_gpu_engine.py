@@ -77,8 +77,9 @@ def test_host_pipeline_matches_device_resident_step():
             assert torch.equal(dY_last, ks.grads["dY"])
 
 
-def _dp_worker(rank, world, port, ret):
+def _dp_worker(rank, world, port, ret, collective):
     import torch.distributed as dist
+    os.environ["KVAE_DP_COLLECTIVE"] = collective
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
@@ -89,9 +90,11 @@ def _dp_worker(rank, world, port, ret):
         case = make_case(Shape(301, 12, 4, 2, 4, 3), seed=9, mask_kind="bernoulli", zero_u=False, c_std=0.3)
         pb, g = _problem(shard_case(case, rank, world), dev)
         ks = KalmanStep(pb, g["eps"], use_graphs=True)
-        for _ in range(2):
+        assert ks.collective == ("nvlink-peer-memory" if collective == "peer" else "nccl"), ks.collective
+        for _ in range(5):                       # replays: the peer exchange alternates its two slots
             t = ks.step()
         torch.cuda.synchronize()
+        assert int(ks.info) == 0
         ret[rank] = dict(elbo=float(t[5]), dA=ks.grads["dA"].cpu(), dC=ks.grads["dC"].cpu(), dY=ks.grads["dY"].cpu(),
                          dalpha=ks.grads["dalpha"].cpu())
     finally:
@@ -99,14 +102,17 @@ def _dp_worker(rank, world, port, ret):
 
 
 @pytest.mark.timeout(300)
-def test_two_gpu_data_parallel_matches_single_gpu():
+@pytest.mark.parametrize("collective", ["peer", "nccl"])
+def test_two_gpu_data_parallel_matches_single_gpu(collective):
+    """collective = "peer": the library's own reduction over NVLink peer memory (kvae_dp_finalize);
+    "nccl": torch.distributed all-reduce + scaling kernels.  Both must reproduce the single-GPU step."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from kalman_vae_b200.dist import shard_bounds
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_dp_worker, args=(2, 29600 + os.getpid() % 300, ret), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, 29600 + os.getpid() % 300 + (7 if collective == "peer" else 0), ret, collective), nprocs=2, join=True)
     dev = torch.device("cuda:0")
     case = make_case(Shape(301, 12, 4, 2, 4, 3), seed=9, mask_kind="bernoulli", zero_u=False, c_std=0.3)
     pb, g = _problem(case, dev)
