@@ -177,6 +177,33 @@ int kvae_dp_destroy(kvae_dp_comm* c);
 int kvae_dp_finalize(const kvae_dims* d, kvae_dp_comm* c, const kvae_grads* g, float* terms, int32_t* info,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * SKVAE regime sampler:  SwitchingDynamicsParameter.compute_batch
+ * kvae/kalman/switch_dyn_param.py:51-79 — the T-step Gumbel-softmax Markov chain over K regimes and its
+ * log q / log p bookkeeping — as one forward and one explicit-adjoint launch (the reference loops over t in Python
+ * with ~12 small ops per step and differentiates them with autograd).  The bi-GRU that produces the logits
+ * (MarkovVariationalRegimePosterior :113-129) stays in PyTorch/cuDNN.
+ *   logits [B,T,K,K] (slice t=0 is never read, :67), init_logits [B,K], gumbel [B,T,K] = -log(Exp(1)) noise drawn by the
+ *   caller (torch.nn.functional.gumbel_softmax draws it internally), trans [K,K] = StickyRegimePrior.transition_matrix.
+ *   Outputs y_seq [B,T,K] (= state_seq, the alpha of the Kalman kernels), log_q [B,T], log_p [B,T].
+ *   hard != 0: straight-through one-hot samples (eval mode, :52 `hard=not is_training`).
+ * The backward entry returns the gradient of  <g_y, y_seq> + <g_logq, log_q> + <g_logp, log_p>  (each g_* may be NULL)
+ * with respect to logits (d_logits [B,T,K,K], slice t=0 zero) and init_logits (d_init [B,K]).  K in 2..8. */
+typedef struct kvae_regime_dims {
+  int32_t B, T, K;
+  int32_t hard;
+  float tau;          /* Gumbel-softmax temperature (switch_dyn_param.py:15: 0.5) */
+} kvae_regime_dims;
+const char* kvae_regime_last_error(void);
+int kvae_regime_supported(int K);
+int kvae_regime_sample_fwd(const kvae_regime_dims* d, const float* logits, const float* init_logits,
+                           const float* gumbel, const float* trans, float* y_seq, float* log_q, float* log_p,
+                           int device, void* stream);
+int kvae_regime_sample_bwd(const kvae_regime_dims* d, const float* logits, const float* init_logits,
+                           const float* gumbel, const float* trans, const float* y_seq, const float* g_y,
+                           const float* g_logq, const float* g_logp, float* d_logits, float* d_init,
+                           int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

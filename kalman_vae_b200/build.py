@@ -68,6 +68,8 @@ def build(force=False, verbose=False):
             f.write("#define KVAE_FOR_EACH_SHAPE(X) " + " ".join(f"X({n},{p},{m},{k})" for (n, p, m, k) in shapes()) + "\n")
         extra = ["--pre-include", hdr]
     jobs.append(([NVCC, *ARCH, *FLAGS, *extra, "-c", os.path.join(CSRC, "kvae_capi.cu"), "-o", o], o))
+    o = os.path.join(OBJ, "regime.o")
+    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_regime.cu"), "-o", o], o))
     o = os.path.join(OBJ, "dp.o")
     jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_dp.cu"), "-o", o], o))
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

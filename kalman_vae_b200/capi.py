@@ -38,6 +38,10 @@ class KvaeGrads(Structure):
     _fields_ = [(k, c_void_p) for k in ("dY", "dU", "dalpha", "dA", "dBm", "dC", "dQ", "dmus", "dSigmas")]
 
 
+class KvaeRegimeDims(Structure):
+    _fields_ = [("B", c_int32), ("T", c_int32), ("K", c_int32), ("hard", c_int32), ("tau", c_float)]
+
+
 class KvaeError(RuntimeError):
     pass
 
@@ -76,6 +80,10 @@ def lib():
     L.kvae_dp_connect.argtypes = [c_void_p, c_void_p]
     L.kvae_dp_destroy.argtypes = [c_void_p]
     L.kvae_dp_finalize.argtypes = [POINTER(KvaeDims), c_void_p, POINTER(KvaeGrads), c_void_p, c_void_p, c_void_p]
+    L.kvae_regime_last_error.restype = c_char_p
+    L.kvae_regime_supported.argtypes = [c_int]
+    L.kvae_regime_sample_fwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 7 + [c_int, c_void_p]
+    L.kvae_regime_sample_bwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 10 + [c_int, c_void_p]
     if L.kvae_abi_version() != 4:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
@@ -86,6 +94,7 @@ EXPORTED_SYMBOLS = [
     "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
     "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
+    "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
     "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize",
 ]
 
@@ -210,3 +219,28 @@ def dp_finalize(dims, comm, grads, terms, info, device):
     grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
     rc = lib().kvae_dp_finalize(byref(dims), comm, byref(grads_s), _ptr(terms, "terms"), _ptr(info, "info"), _stream(device))
     _check_dp(rc, "kvae_dp_finalize")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SKVAE regime sampler (kvae_regime_*)
+# ---------------------------------------------------------------------------------------------------------
+def _check_rg(rc, what):
+    if rc != 0:
+        raise KvaeError(f"{what} failed (status {rc}): {lib().kvae_regime_last_error().decode()}")
+
+
+def regime_fwd(B, T, K, hard, tau, logits, init_logits, gumbel, trans, y_seq, log_q, log_p, device):
+    d = KvaeRegimeDims(B, T, K, int(bool(hard)), float(tau))
+    rc = lib().kvae_regime_sample_fwd(byref(d), _ptr(logits, "logits"), _ptr(init_logits, "init_logits"), _ptr(gumbel, "gumbel"),
+                                      _ptr(trans, "trans"), _ptr(y_seq, "y_seq"), _ptr(log_q, "log_q"), _ptr(log_p, "log_p"),
+                                      device.index, _stream(device))
+    _check_rg(rc, "kvae_regime_sample_fwd")
+
+
+def regime_bwd(B, T, K, hard, tau, logits, init_logits, gumbel, trans, y_seq, g_y, g_logq, g_logp, d_logits, d_init, device):
+    d = KvaeRegimeDims(B, T, K, int(bool(hard)), float(tau))
+    rc = lib().kvae_regime_sample_bwd(byref(d), _ptr(logits, "logits"), _ptr(init_logits, "init_logits"), _ptr(gumbel, "gumbel"),
+                                      _ptr(trans, "trans"), _ptr(y_seq, "y_seq"), _ptr(g_y, "g_y"), _ptr(g_logq, "g_logq"),
+                                      _ptr(g_logp, "g_logp"), _ptr(d_logits, "d_logits"), _ptr(d_init, "d_init"),
+                                      device.index, _stream(device))
+    _check_rg(rc, "kvae_regime_sample_bwd")

@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-from torch.nn.functional import gumbel_softmax
 
 
 class DynamicsParameter(nn.Module):
@@ -179,25 +178,22 @@ class SwitchingDynamicsParameter(nn.Module):
             self.log_pseq = torch.zeros(batch, T, device=dev, dtype=dt)
             self.state_seq = torch.ones(batch, T, 1, device=dev, dtype=dt)
             return self.state_seq
+        if not a_seq.is_cuda:
+            from .capi import KvaeError
+            raise KvaeError("SwitchingDynamicsParameter (B200-native) needs CUDA tensors; there is no CPU path")
+        from .functional import RegimeSampleFunction
         logits, init_logits = self.markov_regime_posterior(a_seq)
-        y0 = gumbel_softmax(init_logits, tau=self.tau, hard=not is_training, dim=-1)
-        log_q0 = torch.log_softmax(init_logits, dim=-1)
-        log_p0 = torch.full_like(log_q0, 1.0 / self.K).log()
-        ys, lq, lp = [y0], [(y0 * log_q0).sum(-1)], [(y0 * log_p0).sum(-1)]
-        trans = self.prior.transition_matrix.to(device=dev, dtype=dt)
-        y_prev = y0
-        for t in range(1, T):
-            l_t = torch.matmul(y_prev.unsqueeze(1), logits[:, t]).squeeze(1)
-            y_t = gumbel_softmax(l_t, tau=self.tau, hard=not is_training, dim=-1)
-            lq.append((y_t * torch.log_softmax(l_t, dim=-1)).sum(-1))
-            tp = torch.matmul(y_prev.unsqueeze(1), trans).squeeze(1)
-            lp.append((y_t * torch.log(tp.clamp_min(1e-8))).sum(-1))
-            ys.append(y_t)
-            y_prev = y_t
-        self.state_seq = torch.stack(ys, 1)
-        self.log_qseq = torch.stack(lq, 1)
-        self.log_pseq = torch.stack(lp, 1)
+        gumbel = self._draw_gumbel(batch, T, self.K, logits)
+        trans = self.prior.transition_matrix.to(device=dev, dtype=torch.float32)
+        # one launch for the whole chain (and one for its adjoint) instead of ~12 ops per time step
+        y_seq, log_q, log_p = RegimeSampleFunction.apply(logits, init_logits, gumbel, trans, float(self.tau), not is_training)
+        self.state_seq, self.log_qseq, self.log_pseq = y_seq, log_q, log_p
         return self.state_seq
+
+    def _draw_gumbel(self, batch, T, K, like):
+        """Gumbel(0,1) noise for every step: the draw torch.nn.functional.gumbel_softmax makes per call
+        (`-empty_like(logits).exponential_().log()`), here for the whole [B,T,K] chain at once."""
+        return -torch.empty(batch, T, K, dtype=like.dtype, device=like.device).exponential_().log()
 
     def compute_batch(self, a_seq, is_training=True):
         """Reference protocol (switch_dyn_param.py:37-92): mixed sequences for callers that want them."""

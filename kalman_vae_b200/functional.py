@@ -287,3 +287,33 @@ class ElboFunction(torch.autograd.Function):
         return (None, None, None, g_extra, gr["dmus"].reshape(ctx.mu_shape), gr["dSigmas"], gr["dY"],
                 gr["dU"] if ctx.has_U else None, gr["dalpha"], gr["dA"], gr["dBm"], gr["dC"],
                 gr["dQ"] if pb.q_per_mode else None)
+
+
+class RegimeSampleFunction(torch.autograd.Function):
+    """(logits [B,T,K,K], init_logits [B,K]) -> (y_seq [B,T,K], log_q [B,T], log_p [B,T]): the Gumbel-softmax regime
+    chain of SwitchingDynamicsParameter.compute_batch (switch_dyn_param.py:51-79) as one launch; backward = one
+    explicit-adjoint launch (csrc/kvae_regime.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits, init_logits, gumbel, trans, tau, hard):
+        B, T, K, _ = logits.shape
+        dev = logits.device
+        lg, il, gn, tr = prep(logits), prep(init_logits), prep(gumbel), prep(trans, dev)
+        y = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+        lq = torch.empty(B, T, dtype=torch.float32, device=dev)
+        lp = torch.empty(B, T, dtype=torch.float32, device=dev)
+        capi.regime_fwd(B, T, K, hard, tau, lg, il, gn, tr, y, lq, lp, dev)
+        ctx.save_for_backward(lg, il, gn, tr, y)
+        ctx.tau, ctx.hard = tau, hard
+        ctx.mark_non_differentiable()
+        return y, lq, lp
+
+    @staticmethod
+    def backward(ctx, g_y, g_lq, g_lp):
+        lg, il, gn, tr, y = ctx.saved_tensors
+        B, T, K, _ = lg.shape
+        dev = lg.device
+        d_logits = torch.empty_like(lg)
+        d_init = torch.empty_like(il)
+        capi.regime_bwd(B, T, K, ctx.hard, ctx.tau, lg, il, gn, tr, y, prep(g_y), prep(g_lq), prep(g_lp), d_logits, d_init, dev)
+        return d_logits, d_init, None, None, None, None

@@ -137,18 +137,8 @@ def test_kvae_imputation_recipe_matches_reference(kind, monkeypatch):
     kf, dyn = _kvae_kalman_block(kind, g)
     a, u, mask = g["a"].to(DEV), g["u"].to(DEV), g["mask"].to(DEV)
     if kind == "switching":
-        noise = g["gumbel_noise"].to(DEV)
-        calls = {"i": 0}
-
-        def det_gumbel_softmax(logits, tau=1.0, hard=False, dim=-1):
-            gn = noise[calls["i"] % noise.shape[0]]
-            calls["i"] += 1
-            y_soft = ((logits + gn) / tau).softmax(dim)
-            if hard:
-                idx = y_soft.max(dim, keepdim=True)[1]
-                return torch.zeros_like(logits).scatter_(dim, idx, 1.0)
-            return y_soft
-        monkeypatch.setattr(dp_mod, "gumbel_softmax", det_gumbel_softmax)
+        noise = g["gumbel_noise"].to(DEV)                       # [T,B,K]: one draw per gumbel_softmax call of the reference
+        dyn._draw_gumbel = lambda b, t, k, like: noise.permute(1, 0, 2).contiguous()
     with torch.no_grad():
         dyn.reset_state()
         outs = kf.smooth(a.clone(), u.clone(), mask)
