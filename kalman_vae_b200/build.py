@@ -13,11 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libkvae_kalman.so")
+# development A/B builds: KVAE_NVCC_FLAGS="-DKV_TPB_LARGE=128" KVAE_LIB_OUT=/path/lib_variant.so (load it with KVAE_LIB=...)
+_VARIANT = os.environ.get("KVAE_LIB_OUT")
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_variant" if _VARIANT else ""))
+LIB = _VARIANT or os.path.join(HERE, "libkvae_kalman.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("KVAE_NVCC_FLAGS", "").split()
 
 
 def shapes():

@@ -93,14 +93,14 @@ template <class C> struct GradAcc {
     KV_UNROLL for (int i = 0; i < nreg; ++i) v[i] = 0.f;
   }
   // dal[k] += <Xbar, X_k> over own rows (caller all-reduces); acc_k += al[k] * Xbar  (or dense store / add)
-  template <int COLS, int OFF, int MODES>
+  template <int COLS, int OFF, int MODES, int LD>
   KV_FN void one(const float* basek, float* dense, int row0, const float (&al)[K], const float (&Xb)[R][COLS], float (&dal)[K],
                  long bt, bool first) {
     KV_UNROLL for (int k = 0; k < MODES; ++k) {
       float s = 0.f;
       KV_UNROLL for (int r = 0; r < R; ++r) {
         float row[COLS];
-        load_row<COLS>(basek + (k * N + row0 + r) * COLS, row);
+        load_row<COLS>(basek + (k * N + row0 + r) * LD, row);
         KV_UNROLL for (int j = 0; j < COLS; ++j) {
           s = fmaf(Xb[r][j], row[j], s);
           if constexpr (!DENSE) v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
@@ -124,20 +124,20 @@ template <class C> struct GradAcc {
     } else { (void)dense; (void)bt; (void)first; }
   }
   KV_FN void addA(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K], long bt, bool first) {
-    one<N, oA, K>(base + Base<C>::oA, dnA, row0, al, Xb, dal, bt, first);
+    one<N, oA, K, Base<C>::ldA>(base + Base<C>::oA, dnA, row0, al, Xb, dal, bt, first);
   }
   KV_FN void addB(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][M], float (&dal)[K], long bt, bool first) {
-    one<M, oB, K>(base + Base<C>::oB, dnB, row0, al, Xb, dal, bt, first);
+    one<M, oB, K, Base<C>::ldB>(base + Base<C>::oB, dnB, row0, al, Xb, dal, bt, first);
   }
   KV_FN void addQ(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][N], float (&dal)[K], long bt, bool first) {
-    if constexpr (C::QPM) one<N, oQ, K>(base + Base<C>::oQ, dnQ, row0, al, Xb, dal, bt, first);
+    if constexpr (C::QPM) one<N, oQ, K, Base<C>::ldQ>(base + Base<C>::oQ, dnQ, row0, al, Xb, dal, bt, first);
   }
   KV_FN void addCt(const float* base, int row0, const float (&al)[K], const float (&Xb)[R][P], float (&dal)[K], long bt, bool first) {
     if constexpr (C::CSH) {
       constexpr int o = DENSE ? 0 : oCt;
       KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < P; ++j) v[o + r * P + j] += Xb[r][j];
     } else {
-      one<P, oCt, K>(base + Base<C>::oCt, dnCt, row0, al, Xb, dal, bt, first);
+      one<P, oCt, K, Base<C>::ldCt>(base + Base<C>::oCt, dnCt, row0, al, Xb, dal, bt, first);
     }
   }
   // zero the dense A/B/Q cotangents of step index bt (t = 0 receives nothing from sweep 3)

@@ -44,7 +44,7 @@ KV_FN bool elbo_const(const Group<C::L, C::R>& g, const float* base, TileRef xbu
   KV_UNROLL for (int a = 0; a < P; ++a) ec.logdetR += logf(ec.LR[a][a]);
   if constexpr (!C::QPM) {
     float Q[R][N], Qs[R][N], dg[R];
-    copy_rows<C, N>(base + Base<C>::oQ, g.row0(), Q);
+    copy_rows<C, N, Base<C>::ldQ>(base + Base<C>::oQ, g.row0(), Q);
     sym_jitter_rows<C>(g, Q, xbuf, jitter, Qs);
     ok = chol_dist<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg) && ok;
     ec.logdetQ = logdet_half<C>(g, dg);

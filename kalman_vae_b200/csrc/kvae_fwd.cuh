@@ -43,12 +43,19 @@ constexpr int pad4(int x) { return (x + 3) & ~3; }
 
 // Base parameters staged once per CTA in shared memory (C^T is stored transposed per mode so that
 // a lane's rows of C_t^T are contiguous).
+// Row stride of a staged base matrix.  Each lane reads ITS OWN rows of A_k/B_k/Q_k/C_k^T when it mixes, i.e. the
+// lanes of a warp read rows that are `cols` floats apart: for cols = 8 or 16 that is a 2-/4-way bank conflict on every
+// 128-bit load (measured for n = 16: 16 wavefronts per LDS.128 instead of 4, half of all shared-memory wavefronts of
+// the forward kernel).  Four floats of padding per row make the eight lanes of a quarter-warp hit disjoint banks.
+template <class C> constexpr int bld(int cols) { return (C::L > 1 && cols % 8 == 0) ? cols + 4 : cols; }
+
 template <class C> struct Base {
+  static constexpr int ldA = bld<C>(C::N), ldB = bld<C>(C::M), ldCt = bld<C>(C::P), ldQ = bld<C>(C::N);
   static constexpr int oA = 0;
-  static constexpr int oB = oA + pad4(C::K * C::N * C::N);
-  static constexpr int oCt = oB + pad4(C::K * C::N * C::M);
-  static constexpr int oQ = oCt + pad4(C::KC * C::N * C::P);
-  static constexpr int oR = oQ + pad4(C::KQ * C::N * C::N);
+  static constexpr int oB = oA + pad4(C::K * C::N * ldA);
+  static constexpr int oCt = oB + pad4(C::K * C::N * ldB);
+  static constexpr int oQ = oCt + pad4(C::KC * C::N * ldCt);
+  static constexpr int oR = oQ + pad4(C::KQ * C::N * ldQ);
   static constexpr int oMu0 = oR + pad4(C::P * C::P);
   static constexpr int oS0 = oMu0 + pad4(C::N);
   static constexpr int total = oS0 + pad4(C::N * C::N);
@@ -61,13 +68,13 @@ KV_FN void base_fill(float* base, int i, const float* A, const float* Bm, const 
   using BL = Base<C>;
   constexpr int N = C::N, P = C::P, M = C::M, K = C::K;
   float v = 0.f;
-  if (i < BL::oB) { if (i < K * N * N) v = A[i]; }
-  else if (i < BL::oCt) { int j = i - BL::oB; if (j < K * N * M) v = Bm[j]; }
+  if (i < BL::oB) { int row = i / BL::ldA, col = i % BL::ldA; if (row < K * N && col < N) v = A[row * N + col]; }
+  else if (i < BL::oCt) { int j = i - BL::oB, row = j / BL::ldB, col = j % BL::ldB; if (row < K * N && col < M) v = Bm[row * M + col]; }
   else if (i < BL::oQ) {
-    int j = i - BL::oCt;
-    if (j < C::KC * N * P) { int k = j / (N * P), rem = j % (N * P), row = rem / P, a = rem % P; v = Cm[(k * P + a) * N + row]; }
+    int j = i - BL::oCt, row = j / BL::ldCt, a = j % BL::ldCt;
+    if (row < C::KC * N && a < P) { int k = row / N, rn = row % N; v = Cm[(k * P + a) * N + rn]; }
   }
-  else if (i < BL::oR) { int j = i - BL::oQ; if (j < C::KQ * N * N) v = Q[j]; }
+  else if (i < BL::oR) { int j = i - BL::oQ, row = j / BL::ldQ, col = j % BL::ldQ; if (row < C::KQ * N && col < N) v = Q[row * N + col]; }
   else if (i < BL::oMu0) { int j = i - BL::oR; if (j < P * P) v = Rm[j]; }
   else if (i < BL::oS0) { int j = i - BL::oMu0; if (j < N) v = mu0[j]; }
   else { int j = i - BL::oS0; if (j < N * N) v = S0[j]; }
@@ -160,36 +167,36 @@ template <class C, bool WITH_YUM> struct InStage {
 // ---------------------------------------------------------------------------------------
 // A.0  mixing: own rows of A_t, B_t, C_t^T, Q_t
 // ---------------------------------------------------------------------------------------
-template <class C, int COLS>
+template <class C, int COLS, int LD = COLS>
 KV_FN void mix_one(const float* __restrict__ basek, int modes, const float (&al)[C::K], int row0, float (&out)[C::R][COLS]) {
   KV_UNROLL for (int r = 0; r < C::R; ++r) KV_UNROLL for (int j = 0; j < COLS; ++j) out[r][j] = 0.f;
   KV_UNROLL for (int k = 0; k < C::K; ++k) {
     if (k < modes) {
       KV_UNROLL for (int r = 0; r < C::R; ++r) {
         float row[COLS];
-        load_row<COLS>(basek + (k * C::N + row0 + r) * COLS, row);
+        load_row<COLS>(basek + (k * C::N + row0 + r) * LD, row);
         KV_UNROLL for (int j = 0; j < COLS; ++j) out[r][j] = fmaf(al[k], row[j], out[r][j]);
       }
     }
   }
 }
-template <class C, int COLS>
+template <class C, int COLS, int LD = COLS>
 KV_FN void copy_rows(const float* __restrict__ src, int row0, float (&out)[C::R][COLS]) {
-  KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<COLS>(src + (row0 + r) * COLS, out[r]);
+  KV_UNROLL for (int r = 0; r < C::R; ++r) load_row<COLS>(src + (row0 + r) * LD, out[r]);
 }
 template <class C> KV_FN void mix_A(const float* base, const float (&al)[C::K], int row0, float (&A)[C::R][C::N]) {
-  mix_one<C, C::N>(base + Base<C>::oA, C::K, al, row0, A);
+  mix_one<C, C::N, Base<C>::ldA>(base + Base<C>::oA, C::K, al, row0, A);
 }
 template <class C> KV_FN void mix_B(const float* base, const float (&al)[C::K], int row0, float (&Bm)[C::R][C::M]) {
-  mix_one<C, C::M>(base + Base<C>::oB, C::K, al, row0, Bm);
+  mix_one<C, C::M, Base<C>::ldB>(base + Base<C>::oB, C::K, al, row0, Bm);
 }
 template <class C> KV_FN void mix_Ct(const float* base, const float (&al)[C::K], int row0, float (&Ct)[C::R][C::P]) {
-  if constexpr (C::CSH) copy_rows<C, C::P>(base + Base<C>::oCt, row0, Ct);
-  else mix_one<C, C::P>(base + Base<C>::oCt, C::K, al, row0, Ct);
+  if constexpr (C::CSH) copy_rows<C, C::P, Base<C>::ldCt>(base + Base<C>::oCt, row0, Ct);
+  else mix_one<C, C::P, Base<C>::ldCt>(base + Base<C>::oCt, C::K, al, row0, Ct);
 }
 template <class C> KV_FN void mix_Q(const float* base, const float (&al)[C::K], int row0, float (&Q)[C::R][C::N]) {
-  if constexpr (C::QPM) mix_one<C, C::N>(base + Base<C>::oQ, C::K, al, row0, Q);
-  else copy_rows<C, C::N>(base + Base<C>::oQ, row0, Q);
+  if constexpr (C::QPM) mix_one<C, C::N, Base<C>::ldQ>(base + Base<C>::oQ, C::K, al, row0, Q);
+  else copy_rows<C, C::N, Base<C>::ldQ>(base + Base<C>::oQ, row0, Q);
 }
 
 // explicit-matrix variants (forward kernels): read the step's rows from dense per-step tensors when given

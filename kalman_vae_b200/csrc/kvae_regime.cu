@@ -18,6 +18,11 @@
 
 namespace {
 
+// One thread per sequence reads its own K*K logits per step: every load instruction of a warp touches 32 different
+// sectors, so the kernels are bound by L1 tag/wavefront throughput per SM, not by latency.  One-warp CTAs spread the
+// warps over all SMs (B = 8192 -> 256 CTAs).
+constexpr int RG_TPB = 32;
+
 template <int K> struct Step {
   float s[K];      // softmax((l+g)/tau)
   float y[K];      // sample (soft: = s; hard: straight-through one-hot)
@@ -34,8 +39,9 @@ __device__ __forceinline__ void sample_step(const float (&l)[K], const float (&g
 #pragma unroll
   for (int k = 0; k < K; ++k) { o.s[k] = expf(x[k] - mx); sum += o.s[k]; }
   int arg = 0;
+  float best = -1.f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) { o.s[k] = o.s[k] / sum; if (o.s[k] > o.s[arg]) arg = k; }   // first maximum, as torch.max
+  for (int k = 0; k < K; ++k) { o.s[k] = o.s[k] / sum; if (o.s[k] > best) { best = o.s[k]; arg = k; } }   // first maximum, as torch.max
 #pragma unroll
   for (int k = 0; k < K; ++k) o.y[k] = hard ? (((k == arg) ? 1.f : 0.f) - o.s[k]) + o.s[k] : o.s[k];
   float ml = -INFINITY;
@@ -50,7 +56,7 @@ __device__ __forceinline__ void sample_step(const float (&l)[K], const float (&g
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) k_regime_fwd(int B, int T, float tau, int hard, const float* __restrict__ logits,
+__global__ void __launch_bounds__(RG_TPB) k_regime_fwd(int B, int T, float tau, int hard, const float* __restrict__ logits,
                                                     const float* __restrict__ init_logits, const float* __restrict__ gumbel,
                                                     const float* __restrict__ trans, float* __restrict__ y_seq,
                                                     float* __restrict__ log_q, float* __restrict__ log_p) {
@@ -61,16 +67,29 @@ __global__ void __launch_bounds__(128) k_regime_fwd(int B, int T, float tau, int
   if (b >= B) return;
   float yp[K];
   const float log_p0 = logf(1.0f / K);
+  // software pipeline: the inputs of step t+1 do not depend on the chain, so they are fetched while step t computes
+  float gn[K], Mn[K * K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) gn[k] = gumbel[(size_t)b * T * K + k];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) Mn[i] = 0.f;
   for (int t = 0; t < T; ++t) {
     const size_t bt = (size_t)b * T + t;
-    float l[K], g[K];
+    float l[K], g[K], M[K * K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) g[k] = gumbel[bt * K + k];
+    for (int k = 0; k < K; ++k) g[k] = gn[k];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) M[i] = Mn[i];
+    if (t + 1 < T) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) gn[k] = gumbel[(bt + 1) * K + k];
+#pragma unroll
+      for (int i = 0; i < K * K; ++i) Mn[i] = logits[(bt + 1) * K * K + i];
+    }
     if (t == 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k) l[k] = init_logits[(size_t)b * K + k];
     } else {
-      const float* M = logits + bt * K * K;
 #pragma unroll
       for (int j = 0; j < K; ++j) l[j] = 0.f;
 #pragma unroll
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(128) k_regime_fwd(int B, int T, float tau, int
 
 // reverse-time adjoint: gradient of  sum <g_y, y_seq> + <g_logq, log_q> + <g_logp, log_p>  w.r.t. logits and init_logits
 template <int K>
-__global__ void __launch_bounds__(128) k_regime_bwd(int B, int T, float tau, int hard, const float* __restrict__ logits,
+__global__ void __launch_bounds__(RG_TPB) k_regime_bwd(int B, int T, float tau, int hard, const float* __restrict__ logits,
                                                     const float* __restrict__ init_logits, const float* __restrict__ gumbel,
                                                     const float* __restrict__ trans, const float* __restrict__ y_seq,
                                                     const float* __restrict__ g_y, const float* __restrict__ g_logq,
@@ -119,19 +138,40 @@ __global__ void __launch_bounds__(128) k_regime_bwd(int B, int T, float tau, int
   float carry[K];   // d/dy_t coming from step t+1
 #pragma unroll
   for (int k = 0; k < K; ++k) carry[k] = 0.f;
-  for (int t = T - 1; t >= 0; --t) {
+  // software pipeline: everything step t-1 reads (y_{t-2}, logits_{t-1}, gumbel_{t-1}, cotangents) is fetched during step t
+  float ypn[K], gn[K], Mn[K * K], gyn[K], qbn, pbn;
+  auto fetch = [&](int t) {
     const size_t bt = (size_t)b * T + t;
-    float yp[K], l[K], g[K], M[K * K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) g[k] = gumbel[bt * K + k];
-    if (t == 0) {
+    for (int k = 0; k < K; ++k) { gn[k] = gumbel[bt * K + k]; gyn[k] = g_y ? g_y[bt * K + k] : 0.f; }
+    qbn = g_logq ? g_logq[bt] : 0.f;
+    pbn = g_logp ? g_logp[bt] : 0.f;
+    if (t > 0) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) { l[k] = init_logits[(size_t)b * K + k]; yp[k] = 0.f; }
+      for (int k = 0; k < K; ++k) ypn[k] = y_seq[(bt - 1) * K + k];
+#pragma unroll
+      for (int i = 0; i < K * K; ++i) Mn[i] = logits[bt * K * K + i];
     } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) yp[k] = y_seq[(bt - 1) * K + k];
+      for (int k = 0; k < K; ++k) ypn[k] = 0.f;
 #pragma unroll
-      for (int i = 0; i < K * K; ++i) M[i] = logits[bt * K * K + i];
+      for (int i = 0; i < K * K; ++i) Mn[i] = 0.f;
+    }
+  };
+  fetch(T - 1);
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t bt = (size_t)b * T + t;
+    float yp[K], l[K], g[K], M[K * K], gy[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { yp[k] = ypn[k]; g[k] = gn[k]; gy[k] = gyn[k]; }
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) M[i] = Mn[i];
+    const float qb = qbn, pb = pbn;
+    if (t > 0) fetch(t - 1);
+    if (t == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) l[k] = init_logits[(size_t)b * K + k];
+    } else {
 #pragma unroll
       for (int j = 0; j < K; ++j) l[j] = 0.f;
 #pragma unroll
@@ -141,10 +181,9 @@ __global__ void __launch_bounds__(128) k_regime_bwd(int B, int T, float tau, int
     }
     Step<K> st;
     sample_step<K>(l, g, tau, hard, st);      // recomputed (bit-identical to the forward launch)
-    const float qb = g_logq ? g_logq[bt] : 0.f, pb = g_logp ? g_logp[bt] : 0.f;
     float yb[K], lb[K], ypb[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) { yb[k] = carry[k] + (g_y ? g_y[bt * K + k] : 0.f); ypb[k] = 0.f; }
+    for (int k = 0; k < K; ++k) { yb[k] = carry[k] + gy[k]; ypb[k] = 0.f; }
     // log_q = sum y lsm
     float sum_lsmb = 0.f;
 #pragma unroll
@@ -216,12 +255,12 @@ int kvae_regime_sample_fwd(const kvae_regime_dims* d, const float* logits, const
   if (d->B <= 0 || d->T <= 0 || !(d->tau > 0.f)) return rg_fail(-1, "B, T, tau must be positive");
   if (!kvae_regime_supported(d->K)) return rg_fail(-2, "K must be in 2..8");
   DevGuard guard(device);
-  const int grid = (d->B + 127) / 128;
+  const int grid = (d->B + RG_TPB - 1) / RG_TPB;
   cudaStream_t s = (cudaStream_t)stream;
   const float it = d->tau;
   (void)cudaGetLastError();
   switch (d->K) {
-#define KV_CASE(k) case k: k_regime_fwd<k><<<grid, 128, 0, s>>>(d->B, d->T, it, d->hard, logits, init_logits, gumbel, trans, y_seq, log_q, log_p); break;
+#define KV_CASE(k) case k: k_regime_fwd<k><<<grid, RG_TPB, 0, s>>>(d->B, d->T, it, d->hard, logits, init_logits, gumbel, trans, y_seq, log_q, log_p); break;
     KV_CASE(2) KV_CASE(3) KV_CASE(4) KV_CASE(5) KV_CASE(6) KV_CASE(7) KV_CASE(8)
 #undef KV_CASE
   }
@@ -236,12 +275,12 @@ int kvae_regime_sample_bwd(const kvae_regime_dims* d, const float* logits, const
   if (d->B <= 0 || d->T <= 0 || !(d->tau > 0.f)) return rg_fail(-1, "B, T, tau must be positive");
   if (!kvae_regime_supported(d->K)) return rg_fail(-2, "K must be in 2..8");
   DevGuard guard(device);
-  const int grid = (d->B + 127) / 128;
+  const int grid = (d->B + RG_TPB - 1) / RG_TPB;
   cudaStream_t s = (cudaStream_t)stream;
   const float it = d->tau;
   (void)cudaGetLastError();
   switch (d->K) {
-#define KV_CASE(k) case k: k_regime_bwd<k><<<grid, 128, 0, s>>>(d->B, d->T, it, d->hard, logits, init_logits, gumbel, trans, y_seq, g_y, g_logq, g_logp, d_logits, d_init); break;
+#define KV_CASE(k) case k: k_regime_bwd<k><<<grid, RG_TPB, 0, s>>>(d->B, d->T, it, d->hard, logits, init_logits, gumbel, trans, y_seq, g_y, g_logq, g_logp, d_logits, d_init); break;
     KV_CASE(2) KV_CASE(3) KV_CASE(4) KV_CASE(5) KV_CASE(6) KV_CASE(7) KV_CASE(8)
 #undef KV_CASE
   }
