@@ -634,6 +634,17 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
     const S4In<C> cu = pf;                                   // this step's inputs (PF: fetched one step ago)
     if constexpr (PF) { if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf); }
     const StepIn<C>& in = cu.in;
+    // the partial dalpha_t / dY_t / dU_t left by sweep 3 are added to at the END of this step: fetch them now so that
+    // the L2 round trip overlaps the step instead of stalling the (in-order) warp right before the stores
+    float da_old[K], dy_old[P], du_old[M];
+    KV_UNROLL for (int k = 0; k < K; ++k) da_old[k] = 0.f;
+    KV_UNROLL for (int q = 0; q < P; ++q) dy_old[q] = 0.f;
+    KV_UNROLL for (int j = 0; j < M; ++j) du_old[j] = 0.f;
+    if (active && g.lane == 0) {
+      load_row<K>(w.dalpha + bt * K, da_old);
+      load_row<P>(w.dY + bt * P, dy_old);
+      if (w.dU) load_row<M>(w.dU + bt * M, du_old);
+    }
     float Sfb[R][N], mfb[R], Spb[R][N], mpb[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
       KV_UNROLL for (int j = 0; j < N; ++j) { Sfb[r][j] = cu.Sfb[r][j] + Sf_carry[r][j]; Spb[r][j] = cu.Spb[r][j]; }
@@ -808,16 +819,13 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
     g.allreduce(red2);
     if (active && g.lane == 0) {
       float da[K], dyv[P];
-      load_row<K>(w.dalpha + bt * K, da);
-      KV_UNROLL for (int k = 0; k < K; ++k) da[k] += red2[k];
+      KV_UNROLL for (int k = 0; k < K; ++k) da[k] = da_old[k] + red2[k];
       store_row<K>(w.dalpha + bt * K, da);
-      load_row<P>(w.dY + bt * P, dyv);
-      KV_UNROLL for (int q = 0; q < P; ++q) dyv[q] += rb[q];
+      KV_UNROLL for (int q = 0; q < P; ++q) dyv[q] = dy_old[q] + rb[q];
       store_row<P>(w.dY + bt * P, dyv);
       if (w.dU) {
         float duv[M];
-        load_row<M>(w.dU + bt * M, duv);
-        KV_UNROLL for (int j = 0; j < M; ++j) duv[j] += red2[K + j];
+        KV_UNROLL for (int j = 0; j < M; ++j) duv[j] = du_old[j] + red2[K + j];
         store_row<M>(w.dU + bt * M, duv);
       }
     }

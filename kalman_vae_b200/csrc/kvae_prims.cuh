@@ -30,6 +30,17 @@ namespace kvae {
 
 // reciprocal square root to ~1 ulp: hardware approximation (MUFU.RSQ, 2 ulp) + one Newton step; one
 // special-function op on the critical path of a Cholesky pivot instead of sqrt followed by a reciprocal
+// reciprocal to ~1 ulp: MUFU.RCP (1 ulp) + one Newton step, no slow-path branch; an LU pivot is on the critical path
+// of every smoother step (four sequential pivots for n = 4), the IEEE division routine costs ~3x the latency
+KV_FN float kv_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float y0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
+  return fmaf(y0, fmaf(-x, y0, 1.0f), y0);
+#else
+  return 1.0f / x;
+#endif
+}
 KV_FN float kv_rsqrt(float s) {
 #if defined(__CUDA_ARCH__)
   const float y0 = rsqrtf(s);
@@ -416,7 +427,7 @@ KV_FN bool lu_dist(const Group<L, R>& g, float (&a)[R][L * R], float (&invu)[L *
     float uk[N];
     KV_UNROLL for (int j = k; j < N; ++j) uk[j] = g.bcast(a[kr][j], owner);
     ok = ok && (uk[k] > 0.f);
-    invu[k] = 1.0f / uk[k];
+    invu[k] = kv_rcp(uk[k]);
     KV_UNROLL for (int r = 0; r < R; ++r) {
       const bool below = (g.row0() + r) > k;
       const float f = below ? a[r][k] * invu[k] : 0.f;
