@@ -270,13 +270,16 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     const bool has_next = (t + 1 < T);
     if constexpr (!PF) load_s3<C>(a, bt, has_next, has_elbo, row0, pf);
     const S3In<C> cu = pf;                                   // this step's inputs (PF: fetched one step ago)
-    if constexpr (PF) { if (has_next) load_s3<C>(a, bt + 1, t + 2 < T, has_elbo, row0, pf); }
     const StepIn<C>& in = cu.in;
     float al1[K], u1[M];
     KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = cu.al1[k];
-    KV_UNROLL for (int j = 0; j < M; ++j) u1[j] = cu.u1[j];
+    // u_{t+1} is first used deep inside the step; "+ 0" makes this the first consumer, so the scoreboard wait of its
+    // (long finished) load happens here and not after the next prefetch has been issued on the same scoreboard
+    KV_UNROLL for (int j = 0; j < M; ++j) u1[j] = cu.u1[j] + 0.0f;
     float A1[R][N];
     mix_A<C>(base, al1, row0, A1);
+    // prefetch of the next step, issued after the mixing loads (see smoother_sweep)
+    if constexpr (PF) { if (has_next) load_s3<C>(a, bt + 1, t + 2 < T, has_elbo, row0, pf); }
     float Ab[R][N], Bb[R][M], Qb[R][N], Ctb[R][P];   // (A,B,Q)-bar at t+1 and C^T-bar at t
     if (has_next) {
       load_rows_opt<R, N>(w.c_A, ((bt + 1) * N + row0) * N, Ab);
@@ -632,7 +635,6 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
     const long bt = (long)b * T + t;
     if constexpr (!PF) load_s4<C>(a, w, base, b, t, row0, pf);
     const S4In<C> cu = pf;                                   // this step's inputs (PF: fetched one step ago)
-    if constexpr (PF) { if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf); }
     const StepIn<C>& in = cu.in;
     // the partial dalpha_t / dY_t / dU_t left by sweep 3 are added to at the END of this step: fetch them now so that
     // the L2 round trip overlaps the step instead of stalling the (in-order) warp right before the stores
@@ -659,6 +661,8 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
     mix_A<C>(base, in.al, row0, A);
     mix_B<C>(base, in.al, row0, Bm);
     mix_Ct<C>(base, in.al, row0, Ct);
+    // prefetch of the next step, issued after the mixing loads (see smoother_sweep)
+    if constexpr (PF) { if (t > 0) load_s4<C>(a, w, base, b, t - 1, row0, pf); }
 
     // recompute the gain
     auto Ct_v = publish<MEM, L, R, P>(g, Ct, CB);

@@ -480,9 +480,11 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       KV_UNROLL for (int j = 0; j < N; ++j) { Sf[r][j] = pf.Sf[r][j]; Sp1[r][j] = pf.Sp1[r][j]; }
       muf[r] = pf.muf[r]; mup1[r] = pf.mup1[r];
     }
-    if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
     float A1[R][N];
     get_A<C>(a, base, al1, row0, bt + 1, A1);
+    // (issued AFTER the mixing loads: directly in front of them the prefetch shared a scoreboard with the LDS of the
+    //  mixing, so the first mixing FMA waited for the whole L2 round trip -- 40 % of this kernel's stall samples)
+    if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
     float J[R][N], LU[R][N], invu[N];
     ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu) && ok;
     // mu_s = mu_f + J (mu_s1 - mu_p1)                                            (:232)
