@@ -287,7 +287,6 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
   if (staged) {
     ins.prefetch(a, g, (long)b * T);
     ins.commit(g);
-    if (T > 4) ins.prefetch(a, g, (long)b * T + 4);
   } else {
     load_step<C>(a, (long)b * T, cur);
   }
@@ -301,6 +300,10 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     get_B<C>(a, base, cur.al, row0, bt, Bm);
     get_Ct<C>(a, base, cur.al, row0, bt, Ct);
     get_Q<C>(a, base, cur.al, row0, bt, Q);
+    // first step of a chunk: start fetching the next chunk.  Issued AFTER the slot / mixing loads: global loads placed
+    // directly in front of shared-memory loads end up on the same scoreboard and the first FMA of the mixing then
+    // waits for the whole L2 round trip (measured: 40 % of the stall samples of this kernel before the reordering)
+    if (staged && (t & 3) == 0 && t + 4 < T) ins.prefetch(a, g, bt + 4);
 
     // predict (A.1): mu_p = A mu + B u ; Sigma_p = (A Sigma) A^T + Q        (kalman_filter.py:65-67)
     float mup[R];
@@ -386,10 +389,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     allgather<MEM, L, R>(g, muf, VB, mu);
     KV_UNROLL for (int r = 0; r < R; ++r) mu_own[r] = muf[r];
     if (staged) {
-      if ((t & 3) == 3 && t + 1 < T) {      // next chunk: publish the pending one, start fetching the one after
-        ins.commit(g);
-        if (t + 5 < T) ins.prefetch(a, g, bt + 5);
-      }
+      if ((t & 3) == 3 && t + 1 < T) ins.commit(g);   // next chunk: publish the pending one
     } else {
       cur = nxt;
     }
@@ -466,10 +466,8 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       StepIn<C> tmp;
       ins.read((t + 1) & 3, tmp);
       KV_UNROLL for (int k = 0; k < C::K; ++k) al1[k] = tmp.al[k];
-      if (((t + 1) & 3) == 0 && t >= 0 && t + 1 >= 4) {   // alpha_{t+1} was the first step of its chunk: switch to the previous chunk
-        ins.commit(g);
-        if (t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
-      }
+      // alpha_{t+1} was the first step of its chunk: switch to the previous chunk (its prefetch follows the mixing)
+      if (((t + 1) & 3) == 0 && t + 1 >= 4) ins.commit(g);
     } else {
       if (a.alpha) load_row<C::K>(a.alpha + (bt + 1) * C::K, al1);
       else { KV_UNROLL for (int k = 0; k < C::K; ++k) al1[k] = 0.f; }
@@ -484,6 +482,7 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     get_A<C>(a, base, al1, row0, bt + 1, A1);
     // (issued AFTER the mixing loads: directly in front of them the prefetch shared a scoreboard with the LDS of the
     //  mixing, so the first mixing FMA waited for the whole L2 round trip -- 40 % of this kernel's stall samples)
+    if (staged && ((t + 1) & 3) == 0 && t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
     if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
     float J[R][N], LU[R][N], invu[N];
     ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu) && ok;
