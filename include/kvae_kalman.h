@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KVAE_ABI_VERSION 4
+#define KVAE_ABI_VERSION 5
 #define KVAE_FLAG_SMOOTH_ONLY 1  /* kvae_dims.flags: forward entry skips the filter sweep (states given) */
 #define KVAE_FLAG_ELBO_ONLY 2    /* kvae_dims.flags: kvae_kf_bwd differentiates the ELBO alone, see kvae_grads */
 #define KVAE_FLAG_WITH_ELBO 4    /* kvae_dims.flags: kvae_kf_bwd also EVALUATES the ELBO (fused value + adjoint), see below */
@@ -92,6 +92,11 @@ typedef struct kvae_states {
   float* Sigmas_pred;   /* [B,T,n,n] */
   float* mus_smooth;    /* [B,T,n]   NULL in the forward pass = filter only */
   float* Sigmas_smooth; /* [B,T,n,n] */
+  /* optional, kvae_kf_mask_partials_count(d) floats: the forward entry writes the per-CTA sums of the mask there
+   * (kalman_filter.py:392 normalises the ELBO by sum(mask)); kvae_kf_bwd with KVAE_FLAG_WITH_ELBO (without RAW_SUMS) that
+   * finds it non-NULL applies 1/max(sum mask,1) inside its sweep instead of re-scaling dY/dalpha/dU afterwards.  It must
+   * come from a forward call on the SAME mask and dims (incl. lanes).  NULL = not used. */
+  float* mask_partials;
 } kvae_states;
 
 int kvae_abi_version(void);
@@ -101,6 +106,9 @@ const char* kvae_last_error(void); /* thread-local, never NULL */
 int kvae_supported(const kvae_dims* d);
 /* lanes per sequence the library would use for this problem size */
 int kvae_pick_lanes(const kvae_dims* d);
+
+/* number of floats of kvae_states.mask_partials for this problem (0 if the shape is not instantiated) */
+size_t kvae_kf_mask_partials_count(const kvae_dims* d);
 
 /* Forward recursion.  A_list [B,T,n,n], B_list [B,T,n,m], C_list [B,T,p,n] may each be NULL
  * (not materialised). */

@@ -26,7 +26,7 @@ class KvaeInputs(Structure):
 
 class KvaeStates(Structure):
     _fields_ = [(k, c_void_p) for k in ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
-                                        "mus_smooth", "Sigmas_smooth")]
+                                        "mus_smooth", "Sigmas_smooth", "mask_partials")]
 
 
 class KvaeCotangents(Structure):
@@ -84,7 +84,9 @@ def lib():
     L.kvae_regime_supported.argtypes = [c_int]
     L.kvae_regime_sample_fwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 7 + [c_int, c_void_p]
     L.kvae_regime_sample_bwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 10 + [c_int, c_void_p]
-    if L.kvae_abi_version() != 4:
+    L.kvae_kf_mask_partials_count.argtypes = [POINTER(KvaeDims)]
+    L.kvae_kf_mask_partials_count.restype = c_size_t
+    if L.kvae_abi_version() != 5:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
     return L
@@ -92,7 +94,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
-    "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
+    "kvae_kf_mask_partials_count", "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
     "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
     "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize",
@@ -147,9 +149,13 @@ def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Si
     return KvaeInputs(*[_ptr(v, k, dev) for k, v in zip(names, vals)])
 
 
-def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None):
-    names = ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "mus_smooth", "Sigmas_smooth")
-    vals = (mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth, Sigmas_smooth)
+def mask_partials_count(dims) -> int:
+    return int(lib().kvae_kf_mask_partials_count(byref(dims)))
+
+
+def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None, mask_partials=None):
+    names = ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "mus_smooth", "Sigmas_smooth", "mask_partials")
+    vals = (mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth, Sigmas_smooth, mask_partials)
     return KvaeStates(*[_ptr(v, k) for k, v in zip(names, vals)])
 
 

@@ -25,6 +25,8 @@ struct BwdArgs {
   float jitter;
   int with_elbo;                    // 1: sweep 3 also accumulates the ELBO value sums (fused forward value: the
                                     //    separate ELBO kernel is not needed; c_elbo then excludes the normaliser)
+  const float* mask_part;           // with_elbo: per-CTA mask sums written by the forward kernel (nullable)
+  int n_mask_part;
   int raw_sums;                     // with_elbo: 1 = leave the gradients un-normalised (data parallel callers apply
                                     //    the GLOBAL 1/max(sum mask,1) after their all-reduce)
   int elbo_only;                    // 1: adjoint of the ELBO alone w.r.t. (mu, Sigma) given as the smoothed states:

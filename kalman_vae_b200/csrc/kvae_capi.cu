@@ -85,6 +85,18 @@ int kvae_kf_filter_smooth_fwd(const kvae_dims* d, const kvae_inputs* in, const k
   return fail(-2, "unsupported shape");
 }
 
+size_t kvae_kf_mask_partials_count(const kvae_dims* d) {
+  if (!d) return 0;
+  kvae_dims dd = *d;
+  if (dd.lanes == 0) dd.lanes = pick_lanes(dd);
+  if (!kvae_supported(&dd)) return 0;
+#define X(n_, p_, m_, k_) \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) return (size_t)kvae::ShapeOps<n_, p_, m_, k_>::fwd_grid(dd);
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return 0;
+}
+
 size_t kvae_kf_elbo_workspace_bytes(const kvae_dims* d) {
   if (!d) return 0;
   kvae_dims dd = *d;

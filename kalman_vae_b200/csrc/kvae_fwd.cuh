@@ -36,6 +36,7 @@ struct Args {
   const float* dC;   // [B,T,P,N]
   const float* dQ;   // [B,T,N,N]  nullable -> base Q
   int smooth_only;   // 1: skip the filter sweep, smooth from the filtered states already in mu_f / Sig_f
+  float* mask_part;  // optional out (forward kernel): per-CTA sum of the mask, see kvae_states.mask_partials
   int* info;  // device word, set to nonzero if a Cholesky pivot was not positive
 };
 
@@ -266,10 +267,12 @@ KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)
 // ---------------------------------------------------------------------------------------
 template <class C>
 KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
-                        float* stage_slot, float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R]) {
+                        float* stage_slot, float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R],
+                        float* msum_out = nullptr) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
   const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), CB = tl.np(0), KB = tl.np(1), VB = tl.vec(0);
+  float msum = 0.f;   // sum_t mask_t of this sequence (the ELBO normaliser's numerator, kalman_filter.py:392)
   const int row0 = g.row0();
   const int T = a.T;
   bool ok = true;
@@ -325,6 +328,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     // update
     auto Ct_v = publish<MEM, L, R, P>(g, Ct, CB);
     GainOut<C> go;
+    msum += cur.m;
     ok = gain<C>(g, base, Sp, mup, Ct, Ct_v, cur.y, cur.m, go) && ok;
     float muf[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -394,6 +398,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
       cur = nxt;
     }
   }
+  if (msum_out) *msum_out = msum;
   if (!ok && active) *a.info = 1;
 }
 

@@ -63,10 +63,27 @@ __global__ void __launch_bounds__(TPB<C>) k_filter_smooth(Args a, BasePtrs bp, i
     for (int r = 0; r < C::R; ++r) load_row<C::N>(a.Sig_f + (btl * C::N + g.row0() + r) * C::N, Sig[r]);
     load_row<C::R>(a.mu_f + btl * C::N + g.row0(), mu_own);
   } else {
-    filter_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own);
+    float msum = 0.f;
+    filter_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own, &msum);
+    if (a.mask_part) {   // per-CTA sum of the mask (fixed order): lets the adjoint apply 1/max(sum mask,1) inside its sweep
+      __shared__ float mred[TPB<C> / 32];
+      float v = (active && g.lane == 0) ? msum : 0.f;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < TPB<C> / 32; ++wq) tot += mred[wq];
+        a.mask_part[blockIdx.x] = tot;
+      }
+    }
   }
   if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu_own);
 }
+
+template <class C> int fwd_grid_of(int B) { return (B + TPB<C> / C::L - 1) / (TPB<C> / C::L); }
 
 template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth, cudaStream_t s) {
   (void)cudaGetLastError();  // do not inherit a stale (non-sticky) error from an earlier call
@@ -276,7 +293,21 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   const bool active = b < a.B;
   if (!active) b = a.B - 1;
   const BTiles<C> tl = warp_tiles<BTiles<C>>(tiles_all, C::L);
-  w.c_elbo = g_elbo ? (*g_elbo) * (w.with_elbo ? 1.0f : terms[6]) : 0.f;
+  float inv_norm = 1.0f;
+  if (w.mask_part) {   // normaliser from the forward kernel's per-CTA mask sums: same fixed-order fp64 sum in every CTA
+    __shared__ double nred[TPB<C> / 32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < w.n_mask_part; i += TPB<C>) v += (double)w.mask_part[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) nred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < TPB<C> / 32; ++wq) tot += nred[wq];
+    inv_norm = (float)(1.0 / (tot < 1.0 ? 1.0 : tot));
+  }
+  w.c_elbo = g_elbo ? (*g_elbo) * (w.with_elbo ? inv_norm : terms[6]) : 0.f;
   GradAcc<C> acc;
   acc.zero();
   acc.on = active;
@@ -451,7 +482,8 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   const int nparam_blocks = (psz + 3) / 4;
   ScaleJob sj{{nullptr, nullptr, nullptr}, {0, 0, 0}};
   int scale_blocks = 0;
-  if (w.with_elbo && !w.raw_sums) {
+  const int no_scale = (w.raw_sums || w.mask_part != nullptr) ? 1 : 0;   // normaliser already inside the sweep (or left out)
+  if (w.with_elbo && !no_scale) {
     sj.p[0] = w.dY; sj.n[0] = (long)BT * C::P;
     sj.p[1] = w.dalpha; sj.n[1] = (long)BT * C::K;
     sj.p[2] = w.dU; sj.n[2] = w.dU ? (long)BT * C::M : 0;
@@ -462,7 +494,7 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   }
   k_bwd_final<<<nparam_blocks + scale_blocks, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
                                                            C::K * C::P * C::N, gp, w.with_elbo ? elbo_partials : nullptr, grid,
-                                                           w.terms_out, w.raw_sums, nparam_blocks, sj);
+                                                           w.terms_out, no_scale, nparam_blocks, sj);
   return (int)cudaGetLastError();
 }
 

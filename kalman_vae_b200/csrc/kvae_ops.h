@@ -13,6 +13,7 @@ struct BwdExtra {
 
 template <int N, int P, int M, int K> struct ShapeOps {
   static bool lanes_ok(int lanes);
+  static int fwd_grid(const kvae_dims& d);
   static int fwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
                  float* C_list, int32_t* info, cudaStream_t s);
   static size_t elbo_ws(const kvae_dims& d);

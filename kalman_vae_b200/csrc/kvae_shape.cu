@@ -29,6 +29,7 @@ Args make_args(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st,
   a.mu_init = in.mu_init; a.Sig_init = in.Sigma_init;
   a.dA = in.A_dense; a.dB = in.B_dense; a.dC = in.C_dense; a.dQ = in.Q_dense;
   a.smooth_only = (d.flags & KVAE_FLAG_SMOOTH_ONLY) ? 1 : 0;
+  a.mask_part = nullptr;
   a.info = info;
   return a;
 }
@@ -37,11 +38,20 @@ BasePtrs make_base(const kvae_inputs& in) { return BasePtrs{in.A, in.Bm, in.C, i
 
 template <> bool ShapeOps<N, P, M, K>::lanes_ok(int lanes) { return KV_L_OK(lanes); }
 
+template <> int ShapeOps<N, P, M, K>::fwd_grid(const kvae_dims& d) {
+#define X(l) \
+  if (d.lanes == (l)) { if constexpr (N % (l) == 0) return fwd_grid_of<Cfg<N, P, M, K, (l), false, false>>(d.B); }
+  KV_FOR_EACH_L(X)
+#undef X
+  return 0;
+}
+
 template <>
 int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list,
                               float* B_list, float* C_list, int32_t* info, cudaStream_t s) {
   Args a = make_args(d, in, st, info);
   a.A_list = A_list; a.B_list = B_list; a.C_list = C_list;
+  if (!a.smooth_only && !in.A_dense) a.mask_part = st.mask_partials;
   const BasePtrs bp = make_base(in);
   const int smooth = (st.mus_smooth != nullptr) ? 1 : 0;
   const bool sw = d.q_per_mode != 0;
@@ -116,6 +126,10 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
   w.with_elbo = (d.flags & KVAE_FLAG_WITH_ELBO) ? 1 : 0;
   w.raw_sums = (d.flags & KVAE_FLAG_RAW_SUMS) ? 1 : 0;
   w.terms_out = x.terms;
+  if (w.with_elbo && !w.raw_sums && !w.elbo_only && st.mask_partials) {
+    w.mask_part = st.mask_partials;
+    w.n_mask_part = fwd_grid(d);
+  }
   w.e_dSig = x.grads->dSigmas; w.e_dmu = x.grads->dmus;
   GradPtrs gp{x.grads->dA, x.grads->dBm, x.grads->dC, x.grads->dQ};
   const bool sw = d.q_per_mode != 0;

@@ -35,6 +35,7 @@ class KalmanStep:
         self.dev = dev
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.st = States(e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n))
+        self.st.mask_partials = e(max(capi.mask_partials_count(pb.dims), 4))
         self.A_list = e(B, T, n, n) if lists else None
         self.B_list = e(B, T, n, m) if lists else None
         self.C_list = e(B, T, p, n) if (lists and not pb.c_shared) else None
@@ -187,7 +188,9 @@ class HostPipeline:
 
     def step(self, Y, U, mask, alpha, eps):
         """Enqueues one step on host tensors (pinned for a truly asynchronous copy).  Returns the slot index to
-        pass to `result()`; does not synchronise."""
+        pass to `result()`; does not synchronise.  U=None / mask=None: nothing is copied for that input and the slot's
+        device-resident tensor is used as it is (zeros / ones from construction -- what the reference creates on the
+        device itself every step, model.py:149-150 and train.py:41)."""
         k = self.i % self.slots
         self.i += 1
         d = self.inputs[k]
@@ -195,7 +198,7 @@ class HostPipeline:
             if self._used[k]:
                 self.copy_stream.wait_event(self.ev_free[k])
             for name, src in (("Y", Y), ("U", U), ("mask", mask), ("alpha", alpha), ("eps", eps)):
-                if d[name] is not None:
+                if d[name] is not None and src is not None:
                     d[name].copy_(src, non_blocking=True)
             self.ev_in[k].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):

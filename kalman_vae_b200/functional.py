@@ -41,6 +41,7 @@ class Problem:
     Sigma_init: Optional[torch.Tensor] = None
     flags: int = 0
     dense: Optional[tuple] = None      # (A [B,T,n,n], B [B,T,n,m], C [B,T,p,n], Q [B,T,n,n] | None): forward only
+    mask_partials: Optional[torch.Tensor] = None   # left by the forward launch of this problem (States.mask_partials)
     dims: object = field(default=None, repr=False)
 
     def __post_init__(self):
@@ -112,10 +113,11 @@ class States:
     Sigmas_pred: torch.Tensor
     mus_smooth: Optional[torch.Tensor] = None
     Sigmas_smooth: Optional[torch.Tensor] = None
+    mask_partials: Optional[torch.Tensor] = None   # per-CTA mask sums of the forward launch (kvae_states.mask_partials)
 
     def c_struct(self):
         return capi.make_states(self.mus_filt, self.Sigmas_filt, self.mus_pred, self.Sigmas_pred,
-                                self.mus_smooth, self.Sigmas_smooth)
+                                self.mus_smooth, self.Sigmas_smooth, self.mask_partials)
 
 
 def smooth_fwd(pb: Problem, smooth=True, lists=True):
@@ -125,6 +127,8 @@ def smooth_fwd(pb: Problem, smooth=True, lists=True):
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     st = States(e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n),
                 e(B, T, n, 1) if smooth else None, e(B, T, n, n) if smooth else None)
+    if smooth and pb.dense is None and not (pb.dims.flags & capi.FLAG_SMOOTH_ONLY):
+        st.mask_partials = e(max(capi.mask_partials_count(pb.dims), 4))
     A_list = e(B, T, n, n) if lists else None
     B_list = e(B, T, n, m) if lists else None
     # shared emission matrix: the reference returns a stack of C[0] (switch_dyn_param.py:85-86);
@@ -188,6 +192,7 @@ class SmoothFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pb: Problem, smooth: bool, Y, U, alpha, A, Bm, C, Q):
         st, A_list, B_list, C_list = smooth_fwd(pb, smooth=smooth, lists=True)
+        pb.mask_partials = st.mask_partials
         ctx.pb, ctx.smooth = pb, smooth
         # outputs are saved through save_for_backward: holding them on ctx directly would create a
         # ctx -> output -> grad_fn -> ctx cycle that only the cyclic GC frees (device memory would pile up)

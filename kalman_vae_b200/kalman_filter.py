@@ -137,7 +137,7 @@ class KalmanFilter(nn.Module):
             mf, Sf, mp, Sp, A_list, B_list = outs[:6]
             C_list = outs[6] if not csh else C[0].expand(B, T, self.p, self.n)
             st = States(mf.detach(), Sf.detach(), mp.detach(), Sp.detach(),
-                        ms.detach() if smooth else None, Ss.detach() if smooth else None)
+                        ms.detach() if smooth else None, Ss.detach() if smooth else None, pb.mask_partials)
         else:
             st, A_list, B_list, C_list = F.smooth_fwd(pb, smooth=smooth, lists=True)
             mf, Sf, mp, Sp = st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_support_table(lib):
     L = capi.lib()
-    assert L.kvae_abi_version() == 4
+    assert L.kvae_abi_version() == 5
     ok = capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 0)
     assert capi.supported(ok)
     assert capi.pick_lanes(ok) == 4                      # small batch -> widest lane group
