@@ -34,7 +34,7 @@ struct BwdArgs {
 };
 
 // Per-warp tiles of the backward sweeps: 8 [n x n] + 3 [n x p] + 2 vector slots.
-template <class C> using BTiles = TileSet<C::L, C::R, C::P, 8, 3, 2, C::MEM>;
+template <class C> using BTiles = TileSet<C::L, C::R, C::P, 7, 3, 2, C::MEM>;
 
 // own entries of a replicated vector
 template <class C> KV_FN void pick_own(const Group<C::L, C::R>& g, const float (&full)[C::N], float (&own)[C::R]) {
@@ -215,7 +215,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
                       int b, bool active, GradAcc<C>& acc, double (&el)[5]) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L, K = C::K;
   constexpr bool MEM = C::MEM;
-  const TileRef T0 = tl.nn(0), T1 = tl.nn(1), T2 = tl.nn(2), T3 = tl.nn(3), T4 = tl.nn(4), T5 = tl.nn(5), TP = tl.nn(7);
+  const TileRef T0 = tl.nn(0), T1 = tl.nn(1), T2 = tl.nn(2), T3 = tl.nn(3), T4 = tl.nn(4), T5 = tl.nn(5), TP = tl.nn(6);
   const TileRef VB = tl.vec(0), VB2 = tl.vec(1);
   // elbo_sample / sym_jitter_rows use Tiles<C> offsets oX0 (= T0) and oV (remapped below)
   const int row0 = g.row0();

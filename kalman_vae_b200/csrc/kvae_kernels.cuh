@@ -19,6 +19,12 @@ namespace kvae {
 #endif
 // (n = 16 with 8 lanes per sequence has 4 groups per warp: its tiles only fit with 2 warps per CTA)
 template <class C> constexpr int TPB = (C::N >= 16) ? (C::L >= 16 ? KV_TPB_LARGE : 64) : KV_TPB_SMALL;
+// backward kernel: for n = 16, L = 16 eight warps per CTA (7 [n x n] tiles per warp + the 33 KB of staged base matrices
+// = 225 KB, 255 registers x 256 threads = the whole register file): ONE CTA per SM either way, so twice the warps
+#ifndef KV_TPB_BWD_LARGE
+#define KV_TPB_BWD_LARGE 256
+#endif
+template <class C> constexpr int TPBB = (C::N >= 16 && C::L >= 16) ? KV_TPB_BWD_LARGE : TPB<C>;
 
 struct BasePtrs { const float *A, *Bm, *C, *Q, *R, *mu0, *S0; };
 
@@ -227,7 +233,7 @@ struct GradPtrs { float *dA, *dB, *dC, *dQ; };
 struct DensePtrs { float *A, *B, *Q, *Ct; };
 
 template <class C> constexpr size_t smem_floats_bwd() {
-  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(TPB<C> / 32) * BTiles<C>::warp_total;
+  constexpr size_t tiles = (size_t)Base<C>::total + (size_t)(TPBB<C> / 32) * BTiles<C>::warp_total;
   constexpr size_t red = (size_t)Base<C>::total + (size_t)GradAcc<C>::PSZ;
   return tiles > red ? tiles : red;
 }
@@ -244,14 +250,14 @@ __device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L
     for (int i = 0; i < GradAcc<C>::nreduce; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], off);
   }
   __syncthreads();   // tiles are dead: reuse them
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) red[i] = 0.f;
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPBB<C>) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int wq = 0; wq < TPB<C> / 32; ++wq) {
+  for (int wq = 0; wq < TPBB<C> / 32; ++wq) {
     if (warp == wq && lane < C::L) acc.for_each(g.row0(), [&](int idx, float v) { red[idx] += v; });
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPB<C>) partial_row[i] = red[i];
+  for (int i = threadIdx.x; i < GradAcc<C>::PSZ; i += TPBB<C>) partial_row[i] = red[i];
 }
 
 // DENSE gradient mode: out[k][e] = sum_{bt in chunk} alpha[bt][k] * X[bt][e]  (one thread per column e, K register
@@ -280,13 +286,13 @@ static __global__ void __launch_bounds__(256) k_mode_contract(const float* __res
 }
 
 template <class C>
-__global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
+__global__ void __launch_bounds__(TPBB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, const float* __restrict__ g_elbo,
                                                   const float* __restrict__ terms, float* __restrict__ partials, DensePtrs dn,
                                                   double* __restrict__ elbo_partials) {
   extern __shared__ f4 smem_raw[];
   float* base = reinterpret_cast<float*>(smem_raw);
   float* tiles_all = stage_base<C>(base, bp);
-  constexpr int GPB = TPB<C> / C::L;
+  constexpr int GPB = TPBB<C> / C::L;
   const int gi = threadIdx.x / C::L;
   const Group<C::L, C::R> g = this_group<C>();
   int b = blockIdx.x * GPB + gi;
@@ -295,16 +301,16 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   const BTiles<C> tl = warp_tiles<BTiles<C>>(tiles_all, C::L);
   float inv_norm = 1.0f;
   if (w.mask_part) {   // normaliser from the forward kernel's per-CTA mask sums: same fixed-order fp64 sum in every CTA
-    __shared__ double nred[TPB<C> / 32];
+    __shared__ double nred[TPBB<C> / 32];
     double v = 0.0;
-    for (int i = threadIdx.x; i < w.n_mask_part; i += TPB<C>) v += (double)w.mask_part[i];
+    for (int i = threadIdx.x; i < w.n_mask_part; i += TPBB<C>) v += (double)w.mask_part[i];
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if ((threadIdx.x & 31) == 0) nred[threadIdx.x >> 5] = v;
     __syncthreads();
     double tot = 0.0;
 #pragma unroll
-    for (int wq = 0; wq < TPB<C> / 32; ++wq) tot += nred[wq];
+    for (int wq = 0; wq < TPBB<C> / 32; ++wq) tot += nred[wq];
     inv_norm = (float)(1.0 / (tot < 1.0 ? 1.0 : tot));
   }
   w.c_elbo = g_elbo ? (*g_elbo) * (w.with_elbo ? inv_norm : terms[6]) : 0.f;
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
   bwd_sweep3<C>(a, w, base, tl, g, b, active, acc, el);
   if (!w.elbo_only) bwd_sweep4<C>(a, w, base, tl, g, b, active, acc);
   if (w.with_elbo) {   // per-CTA partial sums of the ELBO value terms (fixed order -> deterministic)
-    __shared__ double red[TPB<C> / 32][5];
+    __shared__ double red[TPBB<C> / 32][5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       double v = el[i];
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(TPB<C>) k_bwd(Args a, BwdArgs w, BasePtrs bp, 
     if (threadIdx.x < 5) {
       double v = 0.0;
 #pragma unroll
-      for (int wq = 0; wq < TPB<C> / 32; ++wq) v += red[wq][threadIdx.x];
+      for (int wq = 0; wq < TPBB<C> / 32; ++wq) v += red[wq][threadIdx.x];
       elbo_partials[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
     }
   }
@@ -409,7 +415,7 @@ template <class C> inline int contract_chunks(long BT) {
   return (int)n;
 }
 template <class C> size_t bwd_ws_bytes(int B, int T) {
-  constexpr int GPB = TPB<C> / C::L;
+  constexpr int GPB = TPBB<C> / C::L;
   using GA = GradAcc<C>;
   const size_t BT = (size_t)B * T;
   const size_t nn = align256(sizeof(float) * BT * C::N * C::N);
@@ -428,7 +434,7 @@ template <class C> size_t bwd_ws_bytes(int B, int T) {
 template <class C>
 int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo, const float* terms, void* ws,
                GradPtrs gp, cudaStream_t s) {
-  constexpr int GPB = TPB<C> / C::L;
+  constexpr int GPB = TPBB<C> / C::L;
   using GA = GradAcc<C>;
   const size_t sm = sizeof(float) * smem_floats_bwd<C>();
   static bool attr_set = false;
@@ -458,7 +464,7 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   double* elbo_partials = reinterpret_cast<double*>(p); p += align256(sizeof(double) * 5 * (size_t)grid);
   float* partials = reinterpret_cast<float*>(p);
   constexpr int psz = GA::PSZ;
-  constexpr int tpb = TPB<C>;
+  constexpr int tpb = TPBB<C>;
   k_bwd<C><<<grid, tpb, sm, s>>>(a, w, bp, g_elbo, terms, partials, dn, elbo_partials);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
