@@ -402,7 +402,7 @@ def run_cuda(args, rank, local_rank, world):
                        "sharding": "batch dimension, contiguous per rank; ONE exchange per step of a flat buffer [parameter gradients | 5 ELBO sums]",
                        "collective": sets[0].collective},
             "e2e": e2e, "e2e_autograd": e2e_autograd,
-            "gpu_launches": (sets[0].kernel_launches_per_step + (2 if sets[0].peer is not None else 0)) * args.steps,
+            "gpu_launches": sets[0].kernel_launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_bwd launch at this workload from the

@@ -184,6 +184,15 @@ int kvae_dp_connect(kvae_dp_comm* c, const void* handles);
 int kvae_dp_destroy(kvae_dp_comm* c);
 int kvae_dp_finalize(const kvae_dims* d, kvae_dp_comm* c, const kvae_grads* g, float* terms, int32_t* info,
                      void* stream);
+/* The fused form of the two calls above: kvae_kf_bwd (d->flags must hold KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS) whose
+ * final kernel ALSO does what kvae_dp_finalize does -- local reduction of the per-CTA partials, push to every rank,
+ * global normalisation, scaling of dY/dalpha/dU -- so a data-parallel step has the same three launches as a single-GPU
+ * step (k_filter_smooth, k_bwd, k_bwd_final_dp) and no NCCL call.  Same calling discipline as kvae_dp_finalize (every
+ * rank, same number of times, same communicator; do not interleave the two forms on one communicator within a step). */
+int kvae_kf_bwd_dp(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                   const float* eps, float jitter, const float* g_elbo, float* terms,
+                   const kvae_grads* grads, void* workspace, int32_t* info, int device, void* stream,
+                   kvae_dp_comm* comm);
 
 /* ---------------------------------------------------------------------------------------------------------
  * SKVAE regime sampler:  SwitchingDynamicsParameter.compute_batch

@@ -80,6 +80,8 @@ def lib():
     L.kvae_dp_connect.argtypes = [c_void_p, c_void_p]
     L.kvae_dp_destroy.argtypes = [c_void_p]
     L.kvae_dp_finalize.argtypes = [POINTER(KvaeDims), c_void_p, POINTER(KvaeGrads), c_void_p, c_void_p, c_void_p]
+    L.kvae_kf_bwd_dp.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float, c_void_p,
+                                 c_void_p, POINTER(KvaeGrads), c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     L.kvae_regime_last_error.restype = c_char_p
     L.kvae_regime_supported.argtypes = [c_int]
     L.kvae_regime_sample_fwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 7 + [c_int, c_void_p]
@@ -97,7 +99,7 @@ EXPORTED_SYMBOLS = [
     "kvae_kf_mask_partials_count", "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
     "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
-    "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize",
+    "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize", "kvae_kf_bwd_dp",
 ]
 
 
@@ -219,6 +221,15 @@ def dp_connect(comm, handles):
 def dp_destroy(comm):
     if comm:
         lib().kvae_dp_destroy(comm)
+
+
+def bwd_dp(dims, inputs, states, eps, jitter, g_elbo, terms, grads, workspace, info, device, comm):
+    """kvae_kf_bwd + the cross-rank exchange in its final kernel (dims.flags must hold WITH_ELBO | RAW_SUMS)."""
+    grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
+    rc = lib().kvae_kf_bwd_dp(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
+                              _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(grads_s), c_void_p(workspace.data_ptr()),
+                              _ptr(info, "info"), device.index, _stream(device), comm)
+    _check(rc, "kvae_kf_bwd_dp")
 
 
 def dp_finalize(dims, comm, grads, terms, info, device):

@@ -139,9 +139,9 @@ size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d) {
   return 0;
 }
 
-int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
-                const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
-                void* workspace, int32_t* info, int device, void* stream) {
+static int bwd_impl(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                    const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
+                    void* workspace, int32_t* info, int device, void* stream, kvae_dp_comm* comm) {
   kvae_dims dd;
   if (int rc = check_common(d, in, st, &dd)) return rc;
   if (!info || !grads || !workspace) return fail(-1, "null argument");
@@ -161,8 +161,15 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
   } else if (dd.flags & KVAE_FLAG_RAW_SUMS) {
     return fail(-2, "RAW_SUMS without WITH_ELBO");
   }
+  kvae::DpView view;
+  if (comm) {
+    if ((dd.flags & (KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS)) != (KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS) ||
+        (dd.flags & KVAE_FLAG_ELBO_ONLY))
+      return fail(-2, "kvae_kf_bwd_dp needs flags WITH_ELBO | RAW_SUMS (and not ELBO_ONLY)");
+    if (!kvae::kvae_dp_get_view(comm, &view)) return fail(-1, "kvae_kf_bwd_dp: communicator not connected");
+  }
   DeviceGuard guard(device);
-  kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace};
+  kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace, comm ? &view : nullptr};
 #define X(n_, p_, m_, k_)                                                                                   \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
     int rc = kvae::ShapeOps<n_, p_, m_, k_>::bwd(dd, *in, *st, x, info, (cudaStream_t)stream);             \
@@ -173,6 +180,19 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
   KVAE_FOR_EACH_SHAPE(X)
 #undef X
   return fail(-2, "unsupported shape");
+}
+
+int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
+                void* workspace, int32_t* info, int device, void* stream) {
+  return bwd_impl(d, in, st, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device, stream, nullptr);
+}
+
+int kvae_kf_bwd_dp(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                   const float* g_elbo, float* terms, const kvae_grads* grads, void* workspace, int32_t* info,
+                   int device, void* stream, kvae_dp_comm* comm) {
+  if (!comm) return fail(-1, "kvae_kf_bwd_dp: null communicator");
+  return bwd_impl(d, in, st, eps, jitter, g_elbo, terms, nullptr, grads, workspace, info, device, stream, comm);
 }
 
 }  // extern "C"

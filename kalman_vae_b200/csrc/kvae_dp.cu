@@ -28,6 +28,7 @@
 #include <cstring>
 #include <new>
 #include "../../include/kvae_kalman.h"
+#include "kvae_ops.h"
 
 namespace {
 
@@ -161,6 +162,16 @@ struct kvae_dp_comm {
   DpPeers peers;
   bool connected;
 };
+
+namespace kvae {
+bool kvae_dp_get_view(kvae_dp_comm* c, DpView* out) {
+  if (!c || !c->connected) return false;
+  static_assert(HDR_WORDS == KV_DP_HDR_WORDS, "header size");
+  for (int r = 0; r < 16; ++r) out->buf[r] = (r < c->world) ? c->peers.buf[r] : nullptr;
+  out->rank = c->rank; out->world = c->world; out->nf_pad = c->nf_pad; out->nparam = (int)c->nfloats;
+  return true;
+}
+}  // namespace kvae
 
 extern "C" {
 

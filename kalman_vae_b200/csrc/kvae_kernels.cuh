@@ -406,6 +406,133 @@ static __global__ void __launch_bounds__(128) k_bwd_final(const float* __restric
   else if (gp.dQ) gp.dQ[i - nA - nB - nC] = f;
 }
 
+// Data-parallel variant of k_bwd_final (kvae_kf_bwd_dp): the local reduction, the cross-rank exchange over NVLink peer
+// memory (8-byte {value, step} words pushed into every rank's buffer, see csrc/kvae_dp.cu), the GLOBAL normalisation and
+// the scaling of the rank's dY/dalpha/dU in ONE launch:
+//   A  block 0 reduces the per-CTA ELBO partials and pushes the five sums; every parameter warp reduces its element over
+//      the local per-CTA rows and pushes it to all ranks (fire and forget);
+//   B  every block polls (local memory) the five sums of every rank -> global normaliser;
+//   C  parameter warps poll their element from every rank, add in rank order (fp64), scale, store; the other blocks scale
+//      dY / dalpha / dU.  No block waits for another block of the same launch (a warp only needs what it pushed itself
+//      and block 0's sums; block 0 is scheduled first), so partial residency of the grid cannot dead-lock.
+//   The last block to finish advances the rank's step counter (every block has read it by then).
+__device__ __forceinline__ void dp_st_ll(unsigned long long* p, float v, unsigned step) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(step) : "memory");
+}
+__device__ __forceinline__ bool dp_ld_ll(const unsigned long long* p, unsigned step, float& v) {
+  unsigned lo, hi;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p) : "memory");
+    if (hi == step) break;
+    if (clock64() - t0 > 40000000000LL) { v = 0.f; return false; }   // ~20 s: a peer died; do not hang the GPU
+  }
+  v = __uint_as_float(lo);
+  return true;
+}
+static __global__ void __launch_bounds__(128) k_bwd_final_dp(const float* __restrict__ partials, int nblocks, int psz, int nA,
+                                                             int nB, int nC, GradPtrs gp,
+                                                             const double* __restrict__ elbo_partials, int n_elbo_partials,
+                                                             float* __restrict__ terms, int nparam_blocks, ScaleJob sj,
+                                                             DpView dp, int* __restrict__ info) {
+  __shared__ float part[16][5];
+  __shared__ double tot[5];
+  __shared__ int bad;
+  unsigned long long* mine = dp.buf[dp.rank];
+  const unsigned step = (unsigned)mine[0] + 1u;
+  const int s = (int)(step & 1u);
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int world = dp.world;
+  auto word = [&](int dst, int src, int i) {
+    return dp.buf[dst] + KV_DP_HDR_WORDS + ((size_t)(s * world + src)) * dp.nf_pad + i;
+  };
+  if (threadIdx.x == 0) bad = 0;
+  // ---- A: local reductions, pushed to every rank
+  const bool is_param = (int)blockIdx.x < nparam_blocks;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wp;
+  if (blockIdx.x == 0) {
+    for (int q = wp; q < 5; q += 4) {
+      double v = 0.0;
+      for (int k = lane; k < n_elbo_partials; k += 32) v += elbo_partials[(size_t)k * 5 + q];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane < world) dp_st_ll(word(lane, dp.rank, psz + q), (float)v, step);
+    }
+  }
+  if (is_param && i < psz) {
+    double v = 0.0;
+    for (int blk = lane; blk < nblocks; blk += 32) v += (double)partials[(size_t)blk * psz + i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane < world) dp_st_ll(word(lane, dp.rank, i), (float)v, step);
+  }
+  __syncthreads();
+  // ---- B: the five ELBO sums of every rank -> global normaliser
+  if ((int)threadIdx.x < 5 * world) {
+    const int q = threadIdx.x / 5, j = threadIdx.x % 5;
+    float v;
+    if (!dp_ld_ll(word(dp.rank, q, psz + j), step, v)) bad = 1;
+    part[q][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+    for (int r = 0; r < world; ++r) v += (double)part[r][threadIdx.x];
+    tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const double nrm = tot[4] < 1.0 ? 1.0 : tot[4];
+  const float scale = (float)(1.0 / nrm);
+  if (bad) {
+    if (threadIdx.x == 0) *info = 2;
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      for (int j = 0; j < 5; ++j) terms[j] = (float)tot[j];
+      terms[5] = (float)((tot[0] + tot[1] + tot[2] + tot[3]) / nrm);
+      terms[6] = scale;
+      terms[7] = 0.f;
+    }
+    // ---- C
+    if (is_param) {
+      if (i < psz && lane == 0) {
+        double v = 0.0;
+        bool ok = true;
+        for (int r = 0; r < world; ++r) {
+          float x;
+          ok = dp_ld_ll(word(dp.rank, r, i), step, x) && ok;
+          v += (double)x;
+        }
+        if (!ok) *info = 2;
+        const float f = (float)v * scale;
+        if (i < nA) gp.dA[i] = f;
+        else if (i < nA + nB) gp.dB[i - nA] = f;
+        else if (i < nA + nB + nC) gp.dC[i - nA - nB] = f;
+        else if (gp.dQ) gp.dQ[i - nA - nB - nC] = f;
+      }
+    } else {
+      const long nthreads = (long)(gridDim.x - nparam_blocks) * blockDim.x;
+      const long tid = (long)(blockIdx.x - nparam_blocks) * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float* p = sj.p[j];
+        if (!p) continue;
+        const long n4 = sj.n[j] >> 2;
+        f4* p4 = reinterpret_cast<f4*>(p);
+        for (long k = tid; k < n4; k += nthreads) { f4 v = p4[k]; v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; p4[k] = v; }
+        for (long k = (n4 << 2) + tid; k < sj.n[j]; k += nthreads) p[k] *= scale;
+      }
+    }
+  }
+  // ---- the last block to finish advances the step counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned* done = reinterpret_cast<unsigned*>(mine + 1);
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) { *done = 0u; mine[0] = (unsigned long long)step; }
+  }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <class C> inline int contract_chunks(long BT) {
@@ -433,7 +560,7 @@ template <class C> size_t bwd_ws_bytes(int B, int T) {
 
 template <class C>
 int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo, const float* terms, void* ws,
-               GradPtrs gp, cudaStream_t s) {
+               GradPtrs gp, cudaStream_t s, const DpView* dp = nullptr) {
   constexpr int GPB = TPBB<C> / C::L;
   using GA = GradAcc<C>;
   const size_t sm = sizeof(float) * smem_floats_bwd<C>();
@@ -497,6 +624,20 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
     scale_blocks = (int)((total4 + 128 * 8 - 1) / (128 * 8));
     if (scale_blocks < 1) scale_blocks = 1;
     if (scale_blocks > 148 * 8) scale_blocks = 148 * 8;
+  }
+  if (dp) {   // data parallel: reduction + exchange + global normalisation + scaling in one launch
+    if (dp->nparam != psz) return -5;
+    sj.p[0] = w.dY; sj.n[0] = (long)BT * C::P;
+    sj.p[1] = w.dalpha; sj.n[1] = (long)BT * C::K;
+    sj.p[2] = w.dU; sj.n[2] = w.dU ? (long)BT * C::M : 0;
+    const long total4 = (sj.n[0] + sj.n[1] + sj.n[2]) / 4;
+    int sb = (int)((total4 + 128 * 8 - 1) / (128 * 8));
+    if (sb < 1) sb = 1;
+    if (sb > 148 * 8) sb = 148 * 8;
+    k_bwd_final_dp<<<nparam_blocks + sb, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
+                                                      C::K * C::P * C::N, gp, elbo_partials, grid, w.terms_out, nparam_blocks, sj,
+                                                      *dp, a.info);
+    return (int)cudaGetLastError();
   }
   k_bwd_final<<<nparam_blocks + scale_blocks, 128, 0, s>>>(partials, rows, psz, C::K * C::N * C::N, C::K * C::N * C::M,
                                                            C::K * C::P * C::N, gp, w.with_elbo ? elbo_partials : nullptr, grid,

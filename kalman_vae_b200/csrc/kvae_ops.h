@@ -6,9 +6,21 @@
 
 namespace kvae {
 
+// device-side view of a kvae_dp_comm (csrc/kvae_dp.cu): every rank's exchange buffer as mapped in this process.
+// buffer layout (64-bit words): [0] step counter, [1] blocks-done counter, [16 ...] 2 slots x world x nf_pad LL words
+struct DpView {
+  unsigned long long* buf[16];
+  int rank, world;
+  unsigned long long nf_pad;
+  int nparam;
+};
+constexpr int KV_DP_HDR_WORDS = 16;
+bool kvae_dp_get_view(kvae_dp_comm* c, DpView* out);   // false if the communicator is not connected
+
 struct BwdExtra {
   const float* eps; float jitter; const float* g_elbo; float* terms;
   const kvae_cotangents* cot; const kvae_grads* grads; void* workspace;
+  const DpView* dp;   // non-null: kvae_kf_bwd_dp -- the final kernel also does the cross-rank exchange
 };
 
 template <int N, int P, int M, int K> struct ShapeOps {

@@ -136,8 +136,8 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
 #define X(l)                                                                                             \
   if (d.lanes == (l)) {                                                                                  \
     if constexpr (N % (l) == 0) {                                                                        \
-      return sw ? launch_bwd<Cfg<N, P, M, K, (l), true, true>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s)    \
-                : launch_bwd<Cfg<N, P, M, K, (l), false, false>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s); \
+      return sw ? launch_bwd<Cfg<N, P, M, K, (l), true, true>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s, x.dp)    \
+                : launch_bwd<Cfg<N, P, M, K, (l), false, false>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s, x.dp); \
     }                                                                                                    \
   }
   KV_FOR_EACH_L(X)

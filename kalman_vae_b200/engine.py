@@ -66,10 +66,13 @@ class KalmanStep:
         # data parallel: the exchange runs in this library's own kernels over NVLink peer memory (dist.PeerExchange);
         # KVAE_DP_COLLECTIVE=nccl selects the torch.distributed all-reduce + scaling kernels instead
         self.peer = None
+        self.peer_two_launch = False
         self.collective = "none"
         if self.world > 1:
             self.collective = "nccl"
-            if os.environ.get("KVAE_DP_COLLECTIVE", "peer") == "peer":
+            mode = os.environ.get("KVAE_DP_COLLECTIVE", "peer")   # peer: fused into the adjoint's final kernel (kvae_kf_bwd_dp);
+            self.peer_two_launch = (mode == "peer2")                # peer2: kvae_kf_bwd + kvae_dp_finalize; nccl: torch.distributed
+            if mode in ("peer", "peer2"):
                 try:
                     self.peer = kdist.PeerExchange(dev, psz, group)
                     self.collective = "nvlink-peer-memory"
@@ -84,10 +87,15 @@ class KalmanStep:
     def _compute(self):
         capi.filter_smooth_fwd(self.pb.dims, self._inputs, self._states, self.A_list, self.B_list, self.C_list,
                                self.info, self.dev)
-        capi.bwd(self.dims_bwd, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms, None,
-                 self.grads, self.ws_bwd, self.info, self.dev)
-        if self.peer is not None:
-            capi.dp_finalize(self.pb.dims, self.peer.comm, self.grads, self.terms, self.info, self.dev)
+        if self.peer is not None and not self.peer_two_launch:
+            # the final kernel of the adjoint also does the cross-rank exchange (NVLink peer memory)
+            capi.bwd_dp(self.dims_bwd, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms,
+                        self.grads, self.ws_bwd, self.info, self.dev, self.peer.comm)
+        else:
+            capi.bwd(self.dims_bwd, self._inputs, self._states, self.eps, self.jitter, self.g_elbo, self.terms, None,
+                     self.grads, self.ws_bwd, self.info, self.dev)
+            if self.peer is not None:
+                capi.dp_finalize(self.pb.dims, self.peer.comm, self.grads, self.terms, self.info, self.dev)
 
     def _post(self):
         """after the all-reduce: apply the GLOBAL normaliser"""

@@ -90,7 +90,7 @@ def _dp_worker(rank, world, port, ret, collective):
         case = make_case(Shape(301, 12, 4, 2, 4, 3), seed=9, mask_kind="bernoulli", zero_u=False, c_std=0.3)
         pb, g = _problem(shard_case(case, rank, world), dev)
         ks = KalmanStep(pb, g["eps"], use_graphs=True)
-        assert ks.collective == ("nvlink-peer-memory" if collective == "peer" else "nccl"), ks.collective
+        assert ks.collective == ("nvlink-peer-memory" if collective.startswith("peer") else "nccl"), ks.collective
         for _ in range(5):                       # replays: the peer exchange alternates its two slots
             t = ks.step()
         torch.cuda.synchronize()
@@ -102,17 +102,18 @@ def _dp_worker(rank, world, port, ret, collective):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("collective", ["peer", "nccl"])
+@pytest.mark.parametrize("collective", ["peer", "peer2", "nccl"])
 def test_two_gpu_data_parallel_matches_single_gpu(collective):
-    """collective = "peer": the library's own reduction over NVLink peer memory (kvae_dp_finalize);
-    "nccl": torch.distributed all-reduce + scaling kernels.  Both must reproduce the single-GPU step."""
+    """collective = "peer": the exchange over NVLink peer memory fused into the adjoint's final kernel (kvae_kf_bwd_dp);
+    "peer2": the same exchange as two extra launches (kvae_kf_bwd + kvae_dp_finalize); "nccl": torch.distributed
+    all-reduce + scaling kernels.  All must reproduce the single-GPU step."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from kalman_vae_b200.dist import shard_bounds
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_dp_worker, args=(2, 29600 + os.getpid() % 300 + (7 if collective == "peer" else 0), ret, collective), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, 29600 + os.getpid() % 300 + {"peer": 7, "peer2": 13}.get(collective, 0), ret, collective), nprocs=2, join=True)
     dev = torch.device("cuda:0")
     case = make_case(Shape(301, 12, 4, 2, 4, 3), seed=9, mask_kind="bernoulli", zero_u=False, c_std=0.3)
     pb, g = _problem(case, dev)
