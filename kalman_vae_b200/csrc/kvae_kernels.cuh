@@ -447,6 +447,7 @@ static __global__ void __launch_bounds__(128) k_bwd_final_dp(const float* __rest
     return dp.buf[dst] + KV_DP_HDR_WORDS + ((size_t)(s * world + src)) * dp.nf_pad + i;
   };
   if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
   // ---- A: local reductions, pushed to every rank
   const bool is_param = (int)blockIdx.x < nparam_blocks;
   const int i = blockIdx.x * (blockDim.x >> 5) + wp;
@@ -466,18 +467,22 @@ static __global__ void __launch_bounds__(128) k_bwd_final_dp(const float* __rest
     for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane < world) dp_st_ll(word(lane, dp.rank, i), (float)v, step);
   }
-  __syncthreads();
-  // ---- B: the five ELBO sums of every rank -> global normaliser
+  // ---- B: poll (LOCAL memory).  Lane r of a parameter warp waits for rank r's copy of the warp's element while the
+  //         first 5*world threads of the block wait for the ELBO sums: all round trips of a block are in flight together
+  float xr = 0.f;
+  bool okp = true;
+  if (is_param && i < psz && lane < world) okp = dp_ld_ll(word(dp.rank, lane, i), step, xr);
   if ((int)threadIdx.x < 5 * world) {
     const int q = threadIdx.x / 5, j = threadIdx.x % 5;
     float v;
     if (!dp_ld_ll(word(dp.rank, q, psz + j), step, v)) bad = 1;
     part[q][j] = v;
   }
+  if (!okp) bad = 1;
   __syncthreads();
   if (threadIdx.x < 5) {
     double v = 0.0;
-    for (int r = 0; r < world; ++r) v += (double)part[r][threadIdx.x];
+    for (int r = 0; r < world; ++r) v += (double)part[r][threadIdx.x];   // rank order, fp64
     tot[threadIdx.x] = v;
   }
   __syncthreads();
@@ -494,20 +499,16 @@ static __global__ void __launch_bounds__(128) k_bwd_final_dp(const float* __rest
     }
     // ---- C
     if (is_param) {
-      if (i < psz && lane == 0) {
+      if (i < psz) {   // warp-uniform
         double v = 0.0;
-        bool ok = true;
-        for (int r = 0; r < world; ++r) {
-          float x;
-          ok = dp_ld_ll(word(dp.rank, r, i), step, x) && ok;
-          v += (double)x;
+        for (int r = 0; r < world; ++r) v += (double)__shfl_sync(0xffffffffu, xr, r);   // rank order, fp64: same bits on every rank
+        if (lane == 0) {
+          const float f = (float)v * scale;
+          if (i < nA) gp.dA[i] = f;
+          else if (i < nA + nB) gp.dB[i - nA] = f;
+          else if (i < nA + nB + nC) gp.dC[i - nA - nB] = f;
+          else if (gp.dQ) gp.dQ[i - nA - nB - nC] = f;
         }
-        if (!ok) *info = 2;
-        const float f = (float)v * scale;
-        if (i < nA) gp.dA[i] = f;
-        else if (i < nA + nB) gp.dB[i - nA] = f;
-        else if (i < nA + nB + nC) gp.dC[i - nA - nB] = f;
-        else if (gp.dQ) gp.dQ[i - nA - nB - nC] = f;
       }
     } else {
       const long nthreads = (long)(gridDim.x - nparam_blocks) * blockDim.x;
