@@ -261,7 +261,7 @@ __device__ __forceinline__ void cta_reduce_acc(GradAcc<C>& acc, const Group<C::L
 }
 
 // DENSE gradient mode: out[k][e] = sum_{bt in chunk} alpha[bt][k] * X[bt][e]  (one thread per column e, K register
-// accumulators, X streamed once with coalesced loads); partial rows are reduced by k_param_final.
+// accumulators, X streamed once with coalesced loads); partial rows are reduced by k_bwd_final.
 template <int K>
 static __global__ void __launch_bounds__(256) k_mode_contract(const float* __restrict__ alpha, const float* __restrict__ X, long BT,
                                                               int E, int chunk, float* __restrict__ rows, int psz, int foff,

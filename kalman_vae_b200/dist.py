@@ -4,7 +4,13 @@ contiguous per-rank shards (one process per GPU) and the ONLY exchange is one al
       by the GLOBAL number of observed frames (kalman_filter.py:392-400), and
   (b) the flat parameter-gradient buffer (dA,dB,dC[,dQ]; a few hundred KB, latency bound).
 dY / dU / dalpha stay on the rank that owns the sequences.  Forward-only use (imputation) needs no
-collective at all.  torch.distributed is used as is (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+collective at all.
+
+Two implementations of that one exchange:
+  * PeerExchange (default on GPUs, used by engine.KalmanStep): the library's own kernels over NVLink peer memory
+    (csrc/kvae_dp.cu, kvae_kf_bwd_dp) -- torch.distributed only all-gathers the CUDA-IPC handles once at set-up;
+  * globalize_elbo_terms / allreduce_param_grads: torch.distributed all-reduces (NCCL on the GPUs, gloo in the CPU
+    tests), for the autograd route and as the KVAE_DP_COLLECTIVE=nccl comparison path.
 """
 from __future__ import annotations
 

@@ -57,7 +57,6 @@ class KalmanStep:
         # fused value + adjoint launch; under data parallelism the normaliser is applied after the all-reduce
         self.dims_bwd = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.dims.lanes,
                                        capi.FLAG_WITH_ELBO | (capi.FLAG_RAW_SUMS if self.world > 1 else 0))
-        self.ws_elbo = torch.empty(max(capi.elbo_workspace_bytes(pb.dims), 16), dtype=torch.uint8, device=dev)
         self.ws_bwd = torch.empty(max(capi.bwd_workspace_bytes(self.dims_bwd), 16), dtype=torch.uint8, device=dev)
         self.info = info_word(dev)
         self._inputs = pb.inputs()

@@ -23,7 +23,8 @@ for lanes in (4, 2, 1):
     ks = KalmanStep(pb, g["eps"], use_graphs=False)
     from kalman_vae_b200 import capi as _c
     tf = t(lambda: _c.filter_smooth_fwd(ks.pb.dims, ks._inputs, ks._states, ks.A_list, ks.B_list, ks.C_list, ks.info, ks.dev))
-    te = t(lambda: _c.elbo_fwd(ks.pb.dims, ks._inputs, ks._states, ks.eps, ks.jitter, ks.terms, ks.ws_elbo, ks.info, ks.dev))
+    ws_elbo = torch.empty(max(_c.elbo_workspace_bytes(ks.pb.dims), 16), dtype=torch.uint8, device=ks.dev)
+    te = t(lambda: _c.elbo_fwd(ks.pb.dims, ks._inputs, ks._states, ks.eps, ks.jitter, ks.terms, ws_elbo, ks.info, ks.dev))
     tb = t(lambda: _c.bwd(ks.pb.dims, ks._inputs, ks._states, ks.eps, ks.jitter, ks.g_elbo, ks.terms, None, ks.grads, ks.ws_bwd, ks.info, ks.dev))
     n = B * T
     print(f"B={B} T={T} L={lanes}: fwd {tf*1e3:.2f} ms ({440*n/tf/1e9:.0f} GB/s)  elbo {te*1e3:.2f} ms  bwd {tb*1e3:.2f} ms ({316*n/tb/1e9:.0f} GB/s)  "
