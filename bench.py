@@ -236,7 +236,7 @@ def run_cuda(args, rank, local_rank, world):
     value = world * shape.B * shape.T / (ms_step * 1e-3)
 
     # ---- per-kernel durations (CUDA events around each C-ABI call, rotating sets), for the roofline
-    def time_call(fn_name, reps=200):
+    def time_call(fn_name, reps=args.kernel_reps):
         evs = []
         for i in range(3):
             getattr(sets[i % nsets], fn_name)()
@@ -388,7 +388,15 @@ def run_cuda(args, rank, local_rank, world):
         if not args.no_cpu:
             reps = 3
             cpu_val, cpu_times = cpu_steps_per_sec(shape, shape.B, reps)
+            # the same port on ONE host thread, on a 1024-sequence sample
+            nthreads = torch.get_num_threads()
+            torch.set_num_threads(1)
+            try:
+                cpu_1t, _ = cpu_steps_per_sec(shape, 1024, 1)
+            finally:
+                torch.set_num_threads(nthreads)
             cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "value_1_thread": cpu_1t, "sample_1_thread": "1024 of 8192 sequences, torch.set_num_threads(1), one run after warm-up",
                    "sample": f"full {WORKLOAD} batch ({shape.B} sequences x T={shape.T}) smooth+elbo fwd+bwd with the oracle "
                              f"(torch CPU ops in the reference's op order), best of {reps}; os.cpu_count()={os.cpu_count()}"}
         line = {
@@ -447,6 +455,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-reps", type=int, default=200, help="launches per kernel for the roofline's per-kernel timing "
+                    "(use a small number under ncu so that the launch list keeps the step's own proportions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
