@@ -37,7 +37,7 @@ from kalman_vae_b200.synthetic import CONFIGS, Shape, make_case  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 from the committed `ncu --set full` capture
 # (profiles/, latest round); None = not captured
-NCU_TRAFFIC_BYTES = {"k_bwd": 56.0e6, "k_filter_smooth": 20.7e6}   # profiles/r01e_ncu_full_summary_cfg2.csv
+NCU_TRAFFIC_BYTES = {"k_bwd": 54.6e6, "k_filter_smooth": 20.9e6}   # profiles/r01j_ncu_full_summary_cfg2.csv
 
 METRIC = "kalman_filter_smoother_fwd_bwd_sequence_steps_per_sec"
 UNIT = "sequence-steps/s"
