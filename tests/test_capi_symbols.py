@@ -53,3 +53,19 @@ def test_cpu_tensors_raise():
     pb = Problem(c["Y"], c["U"], c["mask"], c["alpha"], c["A"], c["B"], c["C"], c["Q"], c["R"], c["mu0"], c["Sigma0"], False, False)
     with pytest.raises(capi.KvaeError):
         pb.inputs()        # CPU tensors: no CPU implementation exists
+
+
+def test_data_parallel_and_regime_entries_reject_bad_arguments(lib):
+    """kvae_dp_* / kvae_kf_bwd_dp / kvae_regime_*: argument checks run before anything touches a device."""
+    L = capi.lib()
+    assert L.kvae_dp_handle_bytes() == 64                                   # sizeof(cudaIpcMemHandle_t)
+    assert L.kvae_dp_create(0, 0, 0, 10, None, None) < 0                    # null out pointers / world < 1
+    assert b"kvae_dp_create" in L.kvae_dp_last_error()
+    assert L.kvae_dp_connect(None, None) < 0
+    assert L.kvae_dp_finalize(None, None, None, None, None, None) < 0
+    rc = L.kvae_kf_bwd_dp(None, None, None, None, ctypes.c_float(1e-6), None, None, None, None, None, 0, None, None)
+    assert rc < 0 and b"communicator" in L.kvae_last_error()
+    assert L.kvae_kf_mask_partials_count(None) == 0
+    d = capi.make_dims(8192, 20, 4, 2, 4, 3, False, False, 0)
+    assert capi.mask_partials_count(d) == 8192 // (128 // 4)                # one partial per forward CTA (128 threads, L = 4)
+    assert capi.mask_partials_count(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0)) == 0   # shape not instantiated
