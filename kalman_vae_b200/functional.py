@@ -20,6 +20,30 @@ import torch
 from . import capi
 
 
+_supported_cache = {}   # (n,p,m,K,variant,lanes) -> bool: kvae_supported() is pure
+_size_cache = {}        # (kind, dims fields) -> bytes / counts: the workspace-size entry points are pure
+
+
+def _dims_key(kind, d):
+    return (kind, d.B, d.T, d.n, d.p, d.m, d.K, d.q_per_mode, d.c_shared, d.lanes, d.flags)
+
+
+def bwd_workspace_bytes(dims):
+    k = _dims_key("bwd", dims)
+    v = _size_cache.get(k)
+    if v is None:
+        v = _size_cache[k] = capi.bwd_workspace_bytes(dims)
+    return v
+
+
+def mask_partials_count(dims):
+    k = _dims_key("mp", dims)
+    v = _size_cache.get(k)
+    if v is None:
+        v = _size_cache[k] = capi.mask_partials_count(dims)
+    return v
+
+
 @dataclass
 class Problem:
     """Inputs of one call, normalised to contiguous fp32 CUDA tensors."""
@@ -48,7 +72,12 @@ class Problem:
         B, T, p = self.Y.shape
         K, n, m = self.Bm.shape
         self.dims = capi.make_dims(B, T, n, p, m, K, self.q_per_mode, self.c_shared, self.lanes, self.flags)
-        if not capi.supported(self.dims):
+        self._inputs_cache = None
+        key = (n, p, m, K, bool(self.q_per_mode), bool(self.c_shared), int(self.lanes))   # lanes = 0: every count the library may pick is instantiated
+        ok = _supported_cache.get(key)
+        if ok is None:
+            ok = _supported_cache[key] = capi.supported(self.dims)
+        if not ok:
             raise capi.KvaeError(
                 f"shape (n={n}, p={p}, m={m}, K={K}, switching={self.q_per_mode}, lanes={self.lanes}) is not "
                 "instantiated in libkvae_kalman.so; add it to kalman_vae_b200/csrc/kvae_configs.h and rebuild")
@@ -59,10 +88,16 @@ class Problem:
         return d.B, d.T, d.n, d.p, d.m, d.K
 
     def inputs(self, Y=None, U=None):
+        """kvae_inputs for this problem (built once: the tensors of a Problem never change)."""
+        if Y is None and U is None and self._inputs_cache is not None:
+            return self._inputs_cache
         d = self.dense or (None, None, None, None)
-        return capi.make_inputs(self.Y if Y is None else Y, self.U if U is None else U, self.mask, self.alpha,
-                                self.A, self.Bm, self.C, self.Q, self.R, self.mu0, self.Sigma0,
-                                self.mu_init, self.Sigma_init, d[0], d[1], d[2], d[3])
+        c = capi.make_inputs(self.Y if Y is None else Y, self.U if U is None else U, self.mask, self.alpha,
+                             self.A, self.Bm, self.C, self.Q, self.R, self.mu0, self.Sigma0,
+                             self.mu_init, self.Sigma_init, d[0], d[1], d[2], d[3])
+        if Y is None and U is None:
+            self._inputs_cache = c
+        return c
 
 
 def prep(t, device=None):
@@ -128,7 +163,7 @@ def smooth_fwd(pb: Problem, smooth=True, lists=True):
     st = States(e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n),
                 e(B, T, n, 1) if smooth else None, e(B, T, n, n) if smooth else None)
     if smooth and pb.dense is None and not (pb.dims.flags & capi.FLAG_SMOOTH_ONLY):
-        st.mask_partials = e(max(capi.mask_partials_count(pb.dims), 4))
+        st.mask_partials = e(max(mask_partials_count(pb.dims), 4))
     A_list = e(B, T, n, n) if lists else None
     B_list = e(B, T, n, m) if lists else None
     # shared emission matrix: the reference returns a stack of C[0] (switch_dyn_param.py:85-86);
@@ -166,7 +201,7 @@ def adjoint(pb: Problem, st: States, eps=None, jitter=1e-6, g_elbo=None, terms=N
         dims = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.lanes, capi.FLAG_ELBO_ONLY)
     if with_elbo:
         dims = capi.make_dims(B, T, n, p, m, K, pb.q_per_mode, pb.c_shared, pb.lanes, capi.FLAG_WITH_ELBO)
-    ws = workspace(dev, "bwd", capi.bwd_workspace_bytes(dims))
+    ws = workspace(dev, "bwd", bwd_workspace_bytes(dims))
     capi.bwd(dims, pb.inputs(), st.c_struct(), eps, jitter, g_elbo, terms, cot, grads, ws, info_word(dev), dev)
     return grads
 

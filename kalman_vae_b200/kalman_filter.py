@@ -57,6 +57,7 @@ class KalmanFilter(nn.Module):
         self.check_info = check_info    # read the device 'non-positive pivot' flag after elbo()
         self.strict = True              # verify that elbo() sees the same y/mask values as smooth()
         self._mask_cache = None
+        self._prep_cache = {}
 
     # ------------------------------------------------------------------ helpers
     def _mask(self, mask, B, T, ref):
@@ -107,12 +108,24 @@ class KalmanFilter(nn.Module):
         alpha = self._lstm_alpha_batched(Y)
         return alpha, dyn.A, dyn.B, dyn.C, self.Q, False, False
 
+    def _prep_const(self, t, dev):
+        """prep() of a parameter / buffer, cached until the tensor is modified in place or replaced."""
+        key = id(t)
+        hit = self._prep_cache.get(key)
+        if (hit is not None and hit[0] == t._version and hit[1] == t.data_ptr() and hit[2].device == dev
+                and hit[2].shape == t.shape and t.dtype == torch.float32):
+            return hit[2]
+        v = prep(t, dev)
+        self._prep_cache[key] = (t._version, t.data_ptr(), v)
+        return v
+
     def _problem(self, Y, U, mask_t, alpha, A, Bm, C, Q, qpm, csh, mu_init=None, Sigma_init=None):
         dev = Y.device
         if not Y.is_cuda:
             raise F.capi.KvaeError("KalmanFilter (B200-native) needs CUDA tensors; there is no CPU path")
-        return Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), prep(A, dev), prep(Bm, dev), prep(C, dev),
-                       prep(Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), qpm, csh,
+        pc = self._prep_const
+        return Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), pc(A, dev), pc(Bm, dev), pc(C, dev),
+                       pc(Q, dev), pc(self.R, dev), pc(self.mu0, dev), pc(self.Sigma0, dev), qpm, csh,
                        lanes=self.lanes, mu_init=prep(mu_init), Sigma_init=prep(Sigma_init))
 
     def _run(self, Y, U, mask, smooth):
