@@ -259,6 +259,39 @@ def run_cuda(args, rank, local_rank, world):
                                              s.ws_bwd, s.info, s.dev)
         kt["k_filter_smooth"] = time_call("_only_fwd")
         kt["k_bwd(+bwd_final)"] = time_call("_only_bwd")
+    # ---- the same step in the throughput regime (the machine full: B = 262 144 sequences), for the roofline discussion:
+    #      cfg2 itself is 1 024 warps = 11 % of the warp slots and is latency bound
+    thr = None
+    if rank == 0 and world == 1 and not args.no_throughput:
+        big = Shape(262144, shape.T, shape.n, shape.p, shape.m, shape.K, shape.q_per_mode, shape.c_shared)
+        cb = make_case(big, seed=77)
+        gb = {k: (v.to(dev).contiguous() if torch.is_tensor(v) else v) for k, v in cb.items()}
+        pbb = Problem(gb["Y"], gb["U"], gb["mask"], gb["alpha"], gb["A"], gb["B"], gb["C"], gb["Q"], gb["R"], gb["mu0"], gb["Sigma0"],
+                      shape.q_per_mode, shape.c_shared, lanes=lanes)
+        ksb = KalmanStep(pbb, gb["eps"], use_graphs=not args.no_graphs, need_dU=False)
+
+        def ev(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps
+
+        ms_big = ev(ksb.step, 20)
+        ms_fwd = ev(ksb.forward_only, 20)
+        n_big = big.B * big.T
+        thr = {"B": big.B, "T": big.T, "lanes_per_sequence": capi.pick_lanes(pbb.dims) if lanes == 0 else lanes,
+               "ms_per_step": ms_big, "value": n_big / (ms_big * 1e-3), "unit": UNIT,
+               "whole_step_frac": ab["total"] * n_big / (ms_big * 1e-3) / 1e9 / peak,
+               "forward_ms": ms_fwd, "forward_frac": ab["fwd"] * n_big / (ms_fwd * 1e-3) / 1e9 / peak,
+               "note": "same kernels, 32x the cfg2 batch (4 GB touched per step > L2): where HBM is the binding roofline"}
+        del ksb, pbb, gb, cb
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end with pinned HOST inputs
@@ -417,7 +450,8 @@ def run_cuda(args, rank, local_rank, world):
                          # committed ncu --set full capture (profiles/r01d_ncu_full_summary_cfg2.csv); null for other kernels
                          "traffic": NCU_TRAFFIC_BYTES.get(dom.split("(")[0]), "peak_source": peak_src,
                          "algorithmic_bytes_per_seq_step": ab, "kernel_seconds": kt,
-                         "whole_step_frac": ab["total"] * world * shape.B * shape.T / (ms_step * 1e-3) / 1e9 / (peak * world)},
+                         "whole_step_frac": ab["total"] * world * shape.B * shape.T / (ms_step * 1e-3) / 1e9 / (peak * world),
+                         "throughput_regime": thr},
             "cpu_baseline": cpu, "clocks": clocks,
         }
         emit(line)
@@ -455,6 +489,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-throughput", action="store_true", help="skip the B=262144 throughput-regime measurement")
     ap.add_argument("--kernel-reps", type=int, default=200, help="launches per kernel for the roofline's per-kernel timing "
                     "(use a small number under ncu so that the launch list keeps the step's own proportions)")
     args = ap.parse_args()

@@ -19,16 +19,15 @@ struct DeviceGuard {
 };
 bool variant_ok(const kvae_dims& d) { return (d.q_per_mode != 0) == (d.c_shared != 0); }
 
-// smallest instantiated lane count that still gives >= 8 warps per SM, else the widest
+// lanes per sequence.  Measured on B200: for n <= 4 one row per lane (L = n) wins at EVERY batch size (cfg2: 44.7 us
+// vs 53.8 / 75.5 us for L = 2 / 1; cfg3 in full: 4.95 vs 3.67 G seq-steps/s for L = 1; the L = 1 backward kernel spills
+// 4 KB per thread), and for n = 16 L = 16 (fewer spills).  n = 8: smallest count that still gives >= 8 warps per SM.
 int pick_lanes(const kvae_dims& d) {
   const int n = d.n;
-  int cands[3]; int nc = 0;
-  if (n <= 4) { cands[nc++] = 1; if (n >= 2) cands[nc++] = 2; if (n == 4) cands[nc++] = 4; }
-  else if (n == 8) { cands[nc++] = 4; cands[nc++] = 8; }
-  else { cands[nc++] = n; }   // n = 16: one row per lane is faster at every batch size measured (fewer spills)
+  if (n <= 4) return n < 1 ? 1 : n;
+  if (n != 8) return n;
   const long want_threads = 148L * 8 * 32;
-  for (int i = 0; i < nc; ++i) if ((long)d.B * cands[i] >= want_threads) return cands[i];
-  return cands[nc - 1];
+  return ((long)d.B * 4 >= want_threads) ? 4 : 8;
 }
 }  // namespace
 
