@@ -116,6 +116,31 @@ int kvae_kf_filter_smooth_fwd(const kvae_dims* d, const kvae_inputs* in, const k
                               float* A_list, float* B_list, float* C_list,
                               int32_t* info, int device, void* stream);
 
+/* Filter sweep with the LSTM "dynamics parameter network" in the loop: what
+ * KalmanFilter.filter does with DynamicsParameter when observations are missing -- alpha_t =
+ * softmax(head(LSTM_step(y_for_dyn_{t-1}))), y_for_dyn_t = mask_t y_t + (1 - mask_t) C_t mu_{t|t-1}
+ * (kalman_filter.py:142,159,183-185; dyn_param.py:50-56) -- as ONE launch instead of a cuDNN step + ~10 ops + a filter
+ * launch per time step.  in->alpha is ignored; alpha_out [B,T,K] receives the weights (= dyn_params.state_seq).
+ * Weights in torch.nn.LSTM layout (1 layer, gate order i,f,g,o), hidden <= 52; lstm variant (q_per_mode = c_shared = 0),
+ * d->lanes = 0 or n; st->mus_smooth / Sigmas_smooth are not written (run the forward entry with
+ * KVAE_FLAG_SMOOTH_ONLY afterwards).  Forward only. */
+typedef struct kvae_lstm {
+  const float* w_ih;    /* [4*hidden, p]      lstm.weight_ih_l0 */
+  const float* w_hh;    /* [4*hidden, hidden] lstm.weight_hh_l0 */
+  const float* b_ih;    /* [4*hidden] */
+  const float* b_hh;    /* [4*hidden] */
+  const float* w_head;  /* [K, hidden]        head_w.weight */
+  const float* b_head;  /* [K] */
+  const float* h0;      /* [B, hidden] initial state or NULL (zeros) */
+  const float* c0;
+  float* h_out;         /* [B, hidden] final state or NULL */
+  float* c_out;
+  int32_t hidden;
+} kvae_lstm;
+int kvae_kf_filter_lstm_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                            float* A_list, float* B_list, float* C_list, const kvae_lstm* lstm, float* alpha_out,
+                            int32_t* info, int device, void* stream);
+
 /* ELBO of the smoothed posterior with the reparameterised sample z = mu_s + chol(Sigma_s + jitter I) eps.
  * terms[8] (device, fp32): [0] sum log p(z_t|z_{t-1})  [1] sum mask*log p(y_t|z_t)  [2] sum log p(z_0)
  *   [3] sum entropy  [4] sum(mask)  [5] elbo = ([0]+[1]+[2]+[3]) / max([4],1)  [6] 1/max([4],1)  [7] 0

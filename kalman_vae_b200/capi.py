@@ -42,6 +42,11 @@ class KvaeRegimeDims(Structure):
     _fields_ = [("B", c_int32), ("T", c_int32), ("K", c_int32), ("hard", c_int32), ("tau", c_float)]
 
 
+class KvaeLstm(Structure):
+    _fields_ = [(k, c_void_p) for k in ("w_ih", "w_hh", "b_ih", "b_hh", "w_head", "b_head", "h0", "c0", "h_out", "c_out")] + \
+               [("hidden", c_int32)]
+
+
 class KvaeError(RuntimeError):
     pass
 
@@ -65,6 +70,8 @@ def lib():
     L.kvae_pick_lanes.argtypes = [POINTER(KvaeDims)]
     L.kvae_kf_filter_smooth_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates),
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.kvae_kf_filter_lstm_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_void_p,
+                                          c_void_p, POINTER(KvaeLstm), c_void_p, c_void_p, c_int, c_void_p]
     L.kvae_kf_elbo_workspace_bytes.argtypes = [POINTER(KvaeDims)]
     L.kvae_kf_elbo_workspace_bytes.restype = c_size_t
     L.kvae_kf_elbo_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
@@ -96,7 +103,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
-    "kvae_kf_mask_partials_count", "kvae_kf_filter_smooth_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
+    "kvae_kf_mask_partials_count", "kvae_kf_filter_smooth_fwd", "kvae_kf_filter_lstm_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
     "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
     "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize", "kvae_kf_bwd_dp",
@@ -170,6 +177,16 @@ def filter_smooth_fwd(dims, inputs, states, A_list, B_list, C_list, info, device
                                          _ptr(B_list, "B_list"), _ptr(C_list, "C_list"), _ptr(info, "info"),
                                          device.index, _stream(device))
     _check(rc, "kvae_kf_filter_smooth_fwd")
+
+
+def filter_lstm_fwd(dims, inputs, states, A_list, B_list, C_list, lstm_tensors, hidden, alpha_out, info, device):
+    """Filter sweep with the LSTM dynamics network in the loop.  lstm_tensors: dict with w_ih, w_hh, b_ih, b_hh, w_head,
+    b_head (+ optional h0, c0, h_out, c_out)."""
+    ls = KvaeLstm(*[_ptr(lstm_tensors.get(k), "lstm." + k) for k, _ in KvaeLstm._fields_[:-1]], int(hidden))
+    rc = lib().kvae_kf_filter_lstm_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"), _ptr(B_list, "B_list"),
+                                       _ptr(C_list, "C_list"), byref(ls), _ptr(alpha_out, "alpha_out"), _ptr(info, "info"),
+                                       device.index, _stream(device))
+    _check(rc, "kvae_kf_filter_lstm_fwd")
 
 
 def elbo_workspace_bytes(dims) -> int:

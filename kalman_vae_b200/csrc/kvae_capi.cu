@@ -96,6 +96,31 @@ size_t kvae_kf_mask_partials_count(const kvae_dims* d) {
   return 0;
 }
 
+int kvae_kf_filter_lstm_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, float* A_list, float* B_list,
+                            float* C_list, const kvae_lstm* lstm, float* alpha_out, int32_t* info, int device, void* stream) {
+  if (!d || !in || !st || !lstm || !alpha_out || !info) return fail(-1, "null argument");
+  if (d->B <= 0 || d->T <= 0) return fail(-1, "B and T must be positive");
+  if (d->q_per_mode || d->c_shared) return fail(-2, "the LSTM dynamics network belongs to the lstm variant (q_per_mode = c_shared = 0)");
+  if (!in->Y || !in->A || !in->Bm || !in->C || !in->Q || !in->R || !in->mu0 || !in->Sigma0) return fail(-1, "null input tensor");
+  if (in->A_dense) return fail(-2, "explicit per-step matrices cannot be combined with the in-kernel dynamics network");
+  if (!st->mus_filt || !st->Sigmas_filt || !st->mus_pred || !st->Sigmas_pred) return fail(-1, "null state tensor");
+  if (!lstm->w_ih || !lstm->w_hh || !lstm->b_ih || !lstm->b_hh || !lstm->w_head || !lstm->b_head) return fail(-1, "null LSTM weight");
+  if (lstm->hidden < 1 || lstm->hidden > 52) return fail(-2, "hidden size must be in 1..52");
+  kvae_dims dd = *d;
+  if (dd.lanes == 0) dd.lanes = dd.n;
+  DeviceGuard guard(device);
+#define X(n_, p_, m_, k_)                                                                                   \
+  if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
+    int rc = kvae::ShapeOps<n_, p_, m_, k_>::fwd_lstm(dd, *in, *st, A_list, B_list, C_list, *lstm, alpha_out, info, (cudaStream_t)stream); \
+    if (rc > 0) return fail(rc, cudaGetErrorString((cudaError_t)rc));                                       \
+    if (rc < 0) return fail(-2, "shape / lane count not instantiated for the in-kernel LSTM (K > 1, n <= 8, lanes = n)"); \
+    return 0;                                                                                               \
+  }
+  KVAE_FOR_EACH_SHAPE(X)
+#undef X
+  return fail(-2, "unsupported shape");
+}
+
 size_t kvae_kf_elbo_workspace_bytes(const kvae_dims* d) {
   if (!d) return 0;
   kvae_dims dd = *d;

@@ -224,6 +224,7 @@ template <class C> struct GainOut {
   float K0[C::R][C::P];   // unmasked gain rows
   float Kg[C::R][C::P];   // masked gain rows
   float r[C::P];          // innovation (replicated)
+  float yp[C::P];         // predicted observation C mu_p (replicated)
   float Lc[C::P][C::P];   // chol(S) (replicated)
   float invd[C::P];
 };
@@ -258,17 +259,22 @@ KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)
   RegView<P, P> Lv{o.Lc};
   solve_rows_llt<R, P>(o.K0, Lv, o.invd);                                                    // :89
   KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int a = 0; a < P; ++a) o.Kg[r][a] = m * o.K0[r][a];  // :92
-  KV_UNROLL for (int a = 0; a < P; ++a) o.r[a] = y[a] - red[P * P + a];                      // :73-75
+  KV_UNROLL for (int a = 0; a < P; ++a) { o.yp[a] = red[P * P + a]; o.r[a] = y[a] - red[P * P + a]; }   // :73-75
   return ok;
 }
 
 // ---------------------------------------------------------------------------------------
 // sweep 1: filter.  On return Sig (own rows) and mu (replicated) hold the last filtered belief.
 // ---------------------------------------------------------------------------------------
-template <class C>
+// Hook: compile-time extension points of the filter loop (csrc/kvae_lstm.cuh runs the LSTM dynamics network there);
+// NoHook compiles to nothing.
+struct NoHook {
+  static constexpr bool ON = false;
+};
+template <class C, class Hook = NoHook>
 KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
                         float* stage_slot, float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R],
-                        float* msum_out = nullptr) {
+                        float* msum_out = nullptr, Hook* hook = nullptr) {
   constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
   constexpr bool MEM = C::MEM;
   const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), CB = tl.np(0), KB = tl.np(1), VB = tl.vec(0);
@@ -298,6 +304,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     if (staged) ins.read(t & 3, cur);
     else if (t + 1 < T) load_step<C>(a, bt + 1, nxt);  // software prefetch of the next step's inputs
 
+    if constexpr (Hook::ON) hook->before_step(g, bt, cur);   // alpha_t from the in-kernel dynamics network
     float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
     get_A<C>(a, base, cur.al, row0, bt, A);
     get_B<C>(a, base, cur.al, row0, bt, Bm);
@@ -330,6 +337,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     GainOut<C> go;
     msum += cur.m;
     ok = gain<C>(g, base, Sp, mup, Ct, Ct_v, cur.y, cur.m, go) && ok;
+    if constexpr (Hook::ON) hook->after_gain(cur, go);
     float muf[R];
     KV_UNROLL for (int r = 0; r < R; ++r) {
       float s = 0.f;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "kvae_bwd.cuh"
+#include "kvae_lstm.cuh"
 
 namespace kvae {
 
@@ -87,6 +88,54 @@ __global__ void __launch_bounds__(TPB<C>) k_filter_smooth(Args a, BasePtrs bp, i
     }
   }
   if (smooth) smoother_sweep<C>(a, base, tl, g, b, active, stage_slot, Sig, mu_own);
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter sweep with the LSTM dynamics network in the loop (csrc/kvae_lstm.cuh): lstm variant only
+// ------------------------------------------------------------------------------------------------
+template <class C> constexpr size_t smem_bytes_lstm() {
+  return smem_bytes<C>() + sizeof(float) * (size_t)(LstmGeo<C>::total + (TPB<C> / C::L) * LstmGeo<C>::HP);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB<C>) k_filter_lstm(Args a, BasePtrs bp, LstmPtrs lw) {
+  extern __shared__ f4 smem_raw[];
+  float* base = reinterpret_cast<float*>(smem_raw);
+  float* tiles_all = stage_base<C>(base, bp);
+  constexpr int GPB = TPB<C> / C::L;
+  const int gi = threadIdx.x / C::L;
+  const Group<C::L, C::R> g = this_group<C>();
+  int b = blockIdx.x * GPB + gi;
+  const bool active = b < a.B;
+  if (!active) b = a.B - 1;
+  const FTiles<C> tl = warp_tiles<FTiles<C>>(tiles_all, C::L);
+  float* stage_slot = tiles_all + (TPB<C> / 32) * FTiles<C>::warp_total + gi * InStage<C, true>::group_floats;
+  float* lstm_w = tiles_all + (TPB<C> / 32) * FTiles<C>::warp_total + GPB * InStage<C, true>::group_floats;
+  for (int i = threadIdx.x; i < LstmGeo<C>::total; i += TPB<C>) lstm_w[i] = lstm_weight_at<C>(lw, i);
+  __syncthreads();
+  LstmHook<C> hook;
+  hook.W = lstm_w;
+  hook.hbuf = lstm_w + LstmGeo<C>::total + gi * LstmGeo<C>::HP;
+  hook.alpha_out = lw.alpha_out;
+  hook.on = active;
+  hook.init(g, lw, b);
+  float Sig[C::R][C::N], mu[C::N], mu_own[C::R];
+  filter_sweep<C, LstmHook<C>>(a, base, tl, g, b, active, stage_slot, Sig, mu, mu_own, nullptr, &hook);
+  hook.finish(g, lw, b);
+}
+template <class C> int launch_fwd_lstm(const Args& a, const BasePtrs& bp, const LstmPtrs& lw, cudaStream_t s) {
+  (void)cudaGetLastError();
+  constexpr int GPB = TPB<C> / C::L;
+  const size_t sm = smem_bytes_lstm<C>();
+  static bool attr_set = false;
+  if (sm > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_filter_lstm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = (a.B + GPB - 1) / GPB;
+  constexpr int tpb = TPB<C>;
+  k_filter_lstm<C><<<grid, tpb, sm, s>>>(a, bp, lw);
+  return (int)cudaGetLastError();
 }
 
 template <class C> int fwd_grid_of(int B) { return (B + TPB<C> / C::L - 1) / (TPB<C> / C::L); }

@@ -26,6 +26,8 @@ struct BwdExtra {
 template <int N, int P, int M, int K> struct ShapeOps {
   static bool lanes_ok(int lanes);
   static int fwd_grid(const kvae_dims& d);
+  static int fwd_lstm(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
+                      float* C_list, const kvae_lstm& lw, float* alpha_out, int32_t* info, cudaStream_t s);
   static int fwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
                  float* C_list, int32_t* info, cudaStream_t s);
   static size_t elbo_ws(const kvae_dims& d);

@@ -67,6 +67,25 @@ int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const k
   return -3;
 }
 
+// LSTM dynamics in the filter loop: lstm variant, widest lane count, shapes with K > 1 and n <= 8
+template <>
+int ShapeOps<N, P, M, K>::fwd_lstm(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
+                                   float* C_list, const kvae_lstm& lw, float* alpha_out, int32_t* info, cudaStream_t s) {
+#if KV_K > 1 && KV_N <= 8
+  constexpr int LW = N;   // one row per lane
+  if (d.lanes != LW || d.q_per_mode || lw.hidden > 52 || lw.hidden < 1) return -3;
+  Args a = make_args(d, in, st, info);
+  a.alpha = nullptr;
+  a.A_list = A_list; a.B_list = B_list; a.C_list = C_list;
+  const BasePtrs bp = make_base(in);
+  LstmPtrs p{lw.w_ih, lw.w_hh, lw.b_ih, lw.b_hh, lw.w_head, lw.b_head, lw.h0, lw.c0, lw.h_out, lw.c_out, alpha_out, lw.hidden};
+  return launch_fwd_lstm<Cfg<N, P, M, K, LW, false, false>>(a, bp, p, s);
+#else
+  (void)d; (void)in; (void)st; (void)A_list; (void)B_list; (void)C_list; (void)lw; (void)alpha_out; (void)info; (void)s;
+  return -3;
+#endif
+}
+
 template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims& d) {
 #define X(l) \
   if (d.lanes == (l)) { if constexpr (N % (l) == 0) return elbo_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B, d.T); }

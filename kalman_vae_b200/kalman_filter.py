@@ -175,6 +175,9 @@ class KalmanFilter(nn.Module):
         B, T, p = Y.shape
         dev = Y.device
         n, m = self.n, self.m
+        fused = self._run_fused_lstm(Y, U, mask_t, smooth)
+        if fused is not None:
+            return fused
         y_for_dyn = torch.zeros(B, p, device=dev, dtype=Y.dtype)             # kalman_filter.py:142
         mu = prep(self.mu0, dev).expand(B, n).contiguous()
         Sig = prep(self.Sigma0, dev).expand(B, n, n).contiguous()
@@ -201,6 +204,63 @@ class KalmanFilter(nn.Module):
         if not smooth:
             return mf, Sf, mp, Sp, A_list, B_list, C_list
         # smoother sweep over the stored filter states (one launch, no refiltering)
+        pb = Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), prep(dyn.A, dev), prep(dyn.B, dev), prep(dyn.C, dev),
+                     prep(self.Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), False, False,
+                     lanes=self.lanes, flags=F.capi.FLAG_SMOOTH_ONLY)
+        st = States(mf, Sf, mp, Sp, torch.empty_like(mf), torch.empty_like(Sf))
+        F.capi.filter_smooth_fwd(pb.dims, pb.inputs(), st.c_struct(), None, None, None, F.info_word(dev), dev)
+        pb.flags = 0
+        pb.dims.flags = 0
+        prov = _Provenance(pb, st, (Y, U, alpha, dyn.A, dyn.B, dyn.C, None), True)
+        prov.mus_smooth_ref = weakref.ref(st.mus_smooth)
+        prov.Sigmas_smooth_ref = weakref.ref(st.Sigmas_smooth)
+        for t_ in (A_list, B_list, C_list):
+            _tag(t_, prov)
+        return (st.mus_smooth, st.Sigmas_smooth, mf, Sf, mp, Sp, A_list, B_list, C_list)
+
+    def _run_fused_lstm(self, Y, U, mask_t, smooth):
+        """The same recursion as the stepwise loop below in ONE launch: the LSTM cell, the head and the softmax run
+        inside the filter kernel (csrc/kvae_lstm.cuh, kvae_kf_filter_lstm_fwd).  Returns None when the dynamics network
+        is not a plain 1-layer nn.LSTM (hidden <= 52) + Linear head or the shape is not instantiated for it."""
+        dyn = self.dyn_params
+        lstm, head = getattr(dyn, "lstm", None), getattr(dyn, "head_w", None)
+        B, T, p = Y.shape
+        n, m, K = self.n, self.m, dyn.A.size(0)
+        if not (isinstance(lstm, nn.LSTM) and isinstance(head, nn.Linear) and lstm.num_layers == 1 and not lstm.bidirectional
+                and lstm.bias and getattr(lstm, "proj_size", 0) == 0 and lstm.input_size == p and lstm.hidden_size <= 52
+                and head.bias is not None and n <= 8 and K > 1 and self.lanes in (0, n)):
+            return None
+        dev = Y.device
+        H = lstm.hidden_size
+        pb = self._problem(Y, U, mask_t, None, dyn.A, dyn.B, dyn.C, self.Q, False, False)
+        pb.dims.lanes = n
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        mf, Sf, mp, Sp = e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n)
+        A_list, B_list, C_list, alpha = e(B, T, n, n), e(B, T, n, m), e(B, T, p, n), e(B, T, K)
+        w = dict(w_ih=prep(lstm.weight_ih_l0, dev), w_hh=prep(lstm.weight_hh_l0, dev), b_ih=prep(lstm.bias_ih_l0, dev),
+                 b_hh=prep(lstm.bias_hh_l0, dev), w_head=prep(head.weight, dev), b_head=prep(head.bias, dev),
+                 h_out=e(B, H), c_out=e(B, H))
+        if dyn.lstm_state is not None:
+            w["h0"] = prep(dyn.lstm_state[0].reshape(B, H), dev)
+            w["c0"] = prep(dyn.lstm_state[1].reshape(B, H), dev)
+        st = States(mf, Sf, mp, Sp)
+        try:
+            F.capi.filter_lstm_fwd(pb.dims, pb.inputs(), st.c_struct(), A_list, B_list, C_list, w, H, alpha,
+                                   F.info_word(dev), dev)
+        except F.capi.KvaeError as err:
+            if "not instantiated" in str(err) or "unsupported shape" in str(err):
+                return None
+            raise
+        dyn.lstm_state = (w["h_out"].unsqueeze(0), w["c_out"].unsqueeze(0))
+        dyn.state_seq = alpha                                                # kalman_filter.py:188-191
+        if not smooth:
+            return mf, Sf, mp, Sp, A_list, B_list, C_list
+        return self._smooth_from_filtered(Y, U, mask_t, alpha, mf, Sf, mp, Sp, A_list, B_list, C_list)
+
+    def _smooth_from_filtered(self, Y, U, mask_t, alpha, mf, Sf, mp, Sp, A_list, B_list, C_list):
+        """smoother sweep over stored filter states (one launch, no refiltering) + provenance for elbo()"""
+        dyn = self.dyn_params
+        dev = Y.device
         pb = Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), prep(dyn.A, dev), prep(dyn.B, dev), prep(dyn.C, dev),
                      prep(self.Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), False, False,
                      lanes=self.lanes, flags=F.capi.FLAG_SMOOTH_ONLY)

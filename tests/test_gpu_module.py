@@ -242,3 +242,47 @@ def test_elbo_general_form_with_filtered_states_and_lists_from_filter():
     for name, got, want in zip(("dmu", "dSigma", "dY", "dalpha", "dA", "dC"), (gmu, gSig, gY, gal, gA, gC), rg):
         want = want.reshape(got.shape) if name != "dSigma" else 0.5 * (want + want.mT)   # kernel returns the symmetric gradient
         assert rel(got, want) < 2e-4, (name, rel(got, want))
+
+
+def test_lstm_in_the_loop_kernel_matches_stepwise_path():
+    """lstm dynamics + missing observations: the fused launch (LSTM cell, head, softmax and y_for_dyn inside the filter
+    kernel, kvae_kf_filter_lstm_fwd) against the per-step path (cuDNN LSTM step + one filter launch per time step),
+    which is itself pinned to the reference by the kvae_lstm golden above.  Also: state carried across calls."""
+    torch.manual_seed(3)
+    B, T, n, p, m, K = 67, 33, 4, 2, 4, 3
+    A = torch.eye(n).repeat(K, 1, 1) + 0.05 * torch.randn(K, n, n)
+    Bm, C = 0.05 * torch.randn(K, n, m), 0.3 * torch.randn(K, p, n)
+    dyn = DynamicsParameter(A, Bm, C, hidden_lstm=50)
+    with torch.no_grad():
+        dyn.head_w.bias.copy_(torch.randn(K))          # the default bias (0,-10,-10) would pin alpha to mode 0
+        dyn.head_w.weight.mul_(3.0)
+    kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, torch.zeros(n), 20.0 * torch.eye(n), dyn).to(DEV).eval()
+    Y = torch.randn(B, T, p, device=DEV)
+    U = 0.1 * torch.randn(B, T, m, device=DEV)
+    mask = (torch.rand(B, T, device=DEV) < 0.6).float()
+    outs = {}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False             # cuDNN's LSTM would otherwise run its GEMMs in TF32 (1e-3 gates)
+    for mode in ("fused", "stepwise"):
+        if mode == "stepwise":
+            kf._run_fused_lstm = lambda *a, **k: None
+        with torch.no_grad():
+            dyn.reset_state()
+            o1 = kf.smooth(Y, U, mask)
+            alpha1 = dyn.state_seq.clone()
+            dyn.state_seq = []                          # second call continues from the carried LSTM state
+            o2 = kf.filter(Y, U, mask)
+            alpha2 = dyn.state_seq.clone()
+        outs[mode] = (o1, alpha1, o2, alpha2, dyn.lstm_state[0].clone(), dyn.lstm_state[1].clone())
+    torch.backends.cudnn.allow_tf32 = tf32
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    f, s = outs["fused"], outs["stepwise"]
+    assert (f[1] - s[1]).abs().max() < 2e-5 and (f[3] - s[3]).abs().max() < 2e-5          # alpha
+    assert float(f[1].std()) > 0.05                                                        # weights really vary
+    for a, b in zip(f[0], s[0]):
+        assert rel(a, b) < 2e-5
+    for a, b in zip(f[2], s[2]):
+        assert rel(a, b) < 2e-5
+    assert rel(f[4], s[4]) < 2e-5 and rel(f[5], s[5]) < 2e-5                               # carried (h, c)
+    miss = mask == 0                                                                        # mask handling stays bit-exact
+    assert torch.equal(f[0][2][miss], f[0][4][miss])
