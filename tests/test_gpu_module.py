@@ -244,15 +244,17 @@ def test_elbo_general_form_with_filtered_states_and_lists_from_filter():
         assert rel(got, want) < 2e-4, (name, rel(got, want))
 
 
-def test_lstm_in_the_loop_kernel_matches_stepwise_path():
+@pytest.mark.parametrize("shape,hidden", [((4, 2, 4, 3), 50), ((8, 4, 8, 4), 50), ((4, 2, 4, 3), 17)])
+def test_lstm_in_the_loop_kernel_matches_stepwise_path(shape, hidden):
     """lstm dynamics + missing observations: the fused launch (LSTM cell, head, softmax and y_for_dyn inside the filter
     kernel, kvae_kf_filter_lstm_fwd) against the per-step path (cuDNN LSTM step + one filter launch per time step),
     which is itself pinned to the reference by the kvae_lstm golden above.  Also: state carried across calls."""
     torch.manual_seed(3)
-    B, T, n, p, m, K = 67, 33, 4, 2, 4, 3
+    B, T = 67, 33
+    n, p, m, K = shape
     A = torch.eye(n).repeat(K, 1, 1) + 0.05 * torch.randn(K, n, n)
     Bm, C = 0.05 * torch.randn(K, n, m), 0.3 * torch.randn(K, p, n)
-    dyn = DynamicsParameter(A, Bm, C, hidden_lstm=50)
+    dyn = DynamicsParameter(A, Bm, C, hidden_lstm=hidden)
     with torch.no_grad():
         dyn.head_w.bias.copy_(torch.randn(K))          # the default bias (0,-10,-10) would pin alpha to mode 0
         dyn.head_w.weight.mul_(3.0)
