@@ -428,7 +428,26 @@ def run_cuda(args, rank, local_rank, world):
                 cpu_1t, _ = cpu_steps_per_sec(shape, 1024, 1)
             finally:
                 torch.set_num_threads(nthreads)
+            # context: the same op sequence (stock ATen ops + autograd, what the reference executes) on THIS GPU
+            gpu_ref = None
+            try:
+                from oracle import kalman_oracle as ko
+                gcase = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_case(shape, seed=10).items()}
+                ko.smooth_elbo_fwd_bwd(gcase, torch.float32, backward=True)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                ko.smooth_elbo_fwd_bwd(gcase, torch.float32, backward=True)
+                torch.cuda.synchronize(dev)
+                gpu_ref_s = time.perf_counter() - t0
+                del gcase
+                gpu_ref = {"value": shape.B * shape.T / gpu_ref_s, "unit": UNIT, "ms_per_step": gpu_ref_s * 1e3,
+                           "note": "the port's torch op sequence (the reference's stock-ATen path incl. autograd) run with CUDA "
+                                   "tensors on this B200, full cfg2 batch, wall clock of the second run: kernel-launch bound "
+                                   "(~10^4 launches per step)"}
+            except Exception as err:   # context only: never let it break the bench line
+                gpu_ref = {"value": None, "note": f"not measured: {type(err).__name__}: {err}"[:300]}
             cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "reference_ops_on_this_gpu": gpu_ref,
                    "value_1_thread": cpu_1t, "sample_1_thread": "1024 of 8192 sequences, torch.set_num_threads(1), one run after warm-up",
                    "sample": f"full {WORKLOAD} batch ({shape.B} sequences x T={shape.T}) smooth+elbo fwd+bwd with the oracle "
                              f"(torch CPU ops in the reference's op order), best of {reps}; os.cpu_count()={os.cpu_count()}"}

@@ -52,7 +52,7 @@ def mix(alpha, A, Bm, C, Q, c_shared: bool, q_per_mode: bool):
 def filter_step(mu, Sigma, y, u, A, Bm, C, Q, R, m_t):
     """mu [B,n,1], Sigma [B,n,n], y [B,p,1], u [B,m,1], m_t [B]."""
     n = Sigma.shape[-1]
-    I = torch.eye(n, dtype=Sigma.dtype)
+    I = torch.eye(n, dtype=Sigma.dtype, device=Sigma.device)
     mu_p = (A @ mu) + (Bm @ u)                                   # :65
     Sig_p = A @ Sigma @ A.mT + Q                                 # :67 (not symmetrised)
     r = y - C @ mu_p                                             # :73-75
@@ -113,7 +113,7 @@ def smooth(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, c_shared, q_per_mode)
 def safe_cholesky(Sigma, max_tries=5, jitter_init=1e-6):
     n = Sigma.shape[-1]
     Sigma = 0.5 * (Sigma + Sigma.mT)
-    eye = torch.eye(n, dtype=Sigma.dtype)
+    eye = torch.eye(n, dtype=Sigma.dtype, device=Sigma.device)
     jitter = jitter_init
     for _ in range(max_tries):
         L, info = torch.linalg.cholesky_ex(Sigma + jitter * eye)
