@@ -130,6 +130,13 @@ def cpu_steps_per_sec(shape: Shape, sample_B: int, reps: int, warmup: int = 1):
     return sample_B * shape.T / best, times
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs run on rank 0 alone and may use the whole host."""
+    n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+
+
 def run_reference(args, rank, world):
     """Times the reference algorithm (CPU port, all host threads).  Each step is a bounded sample of the
     cfg2 batch, sized from a short calibration so that warmup+steps finish in about two minutes."""
@@ -137,6 +144,7 @@ def run_reference(args, rank, world):
         return
     from oracle import kalman_oracle as ko
     shape = CONFIGS[WORKLOAD]
+    use_all_host_threads()
     threads = torch.get_num_threads()
     t0 = time.perf_counter()
     calib = make_case(Shape(512, shape.T, shape.n, shape.p, shape.m, shape.K), seed=10)
@@ -419,6 +427,7 @@ def run_cuda(args, rank, local_rank, world):
         cpu_val, cpu_times = (None, [])
         cpu = None
         if not args.no_cpu:
+            use_all_host_threads()
             reps = 3
             cpu_val, cpu_times = cpu_steps_per_sec(shape, shape.B, reps)
             # the same port on ONE host thread, on a 1024-sequence sample
