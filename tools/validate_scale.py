@@ -63,7 +63,12 @@ else:
         gel = torch.ones(1, device=dev)
         gr = F.adjoint(pb, st, eps=g["eps"], g_elbo=gel, terms=terms, need_dU=False)
         tb = ev_time(lambda: F.adjoint(pb, st, eps=g["eps"], g_elbo=gel, terms=terms, need_dU=False), 2)
+        # the fused training step (k_filter_smooth, k_bwd with the ELBO value, k_bwd_final) in one CUDA graph
+        from kalman_vae_b200.engine import KalmanStep
+        ks = KalmanStep(pb, g["eps"], use_graphs=True, need_dU=False)
+        tstep = ev_time(ks.step, 3)
         B, T = shape.B, shape.T
         finite = all(bool(torch.isfinite(v).all()) for v in gr.values() if v is not None)
         print(json.dumps(dict(B=B, T=T, lanes=lanes, fwd_s=tf, elbo_s=te, bwd_s=tb, seq_steps_per_s=B * T / (tf + te + tb),
-                              alg_GBps=9032 * B * T / (tf + te + tb) / 1e9, elbo=float(terms[5]), info=int(F.info_word(dev)), finite=finite)), flush=True)
+                              alg_GBps=9032 * B * T / (tf + te + tb) / 1e9, fused_step_s=tstep, fused_seq_steps_per_s=B * T / tstep,
+                              fused_elbo=float(ks.terms[5]), elbo=float(terms[5]), info=int(F.info_word(dev)), finite=finite)), flush=True)
