@@ -296,6 +296,34 @@ class KalmanFilter(nn.Module):
         """kalman_filter.py:240-279 -> 9-tuple (mus_smooth, Sigmas_smooth, mus_filt, ..., C_list)"""
         return self._run(Y, U, mask, smooth=True)
 
+    @torch.no_grad()
+    def impute_observations(self, Y, U, mask=None):
+        """The Kalman part of KVAE.impute (model.py:267-288) without materialising the per-step
+        matrices: smooth, then  a_imputed = C_t mu_{t|T},  a_filtered = C_t mu_{t|t}  straight from the mixture weights
+        (`(C_list @ mus).squeeze(-1)` in the reference).  The forward launch skips A_list / B_list / C_list (160 of its 440
+        output bytes per sequence-step at the KVAE shapes).  Returns (a_imputed [B,T,p], a_filtered [B,T,p],
+        mus_smooth [B,T,n,1], mus_filt [B,T,n,1]).  Forward only, like the reference's impute()."""
+        B, T, _ = Y.shape
+        mask_t = self._mask(mask, B, T, Y)
+        dyn = self.dyn_params
+        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and not self._mask_is_ones(mask_t):
+            outs = self._run_stepwise_lstm(Y, U, mask_t, True)          # fused LSTM launch (or the per-step fallback)
+            ms, mf, alpha, csh = outs[0], outs[2], dyn.state_seq, False
+        else:
+            alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
+            pb = self._problem(Y, U, mask_t, alpha, A, Bm, C, Q, qpm, csh)
+            st, _, _, _ = F.smooth_fwd(pb, smooth=True, lists=False)
+            ms, mf = st.mus_smooth, st.mus_filt
+        Cp = dyn.C.detach().to(torch.float32)
+        if csh:
+            proj = lambda mu: mu.squeeze(-1) @ Cp[0].T
+        else:   # sum_k alpha_k (C_k mu): one GEMM [B*T,n] x [n,K*p] and a weighted sum over the modes
+            K, p, n = Cp.shape
+            Cflat = Cp.reshape(K * p, n).T
+            al = alpha.to(torch.float32).unsqueeze(-1)
+            proj = lambda mu: ((mu.squeeze(-1) @ Cflat).view(B, T, K, p) * al).sum(2)
+        return proj(ms), proj(mf), ms, mf
+
     def elbo(self, mu_t_T, Sigma_t_T, y_t, u_t, A_list, B_list, C_list, Q_list=None, mask=None):
         """kalman_filter.py:305-401.  The standard-normal draw of `rsample` (:351) is made here with
         the same torch call the reference ends up in (`torch.empty(B,T,n).normal_()`)."""

@@ -152,6 +152,12 @@ def test_kvae_imputation_recipe_matches_reference(kind, monkeypatch):
     a_filtered = (outs[8] @ outs[2]).squeeze(-1)                            # model.py:287-288
     assert torch.allclose(a_imputed.cpu(), g["a_imputed"], rtol=1e-4, atol=1e-6)
     assert torch.allclose(a_filtered.cpu(), g["a_filtered"], rtol=1e-4, atol=1e-6)
+    # the same two quantities without materialising A_list / B_list / C_list
+    dyn.reset_state()
+    ai, af, ms2, mf2 = kf.impute_observations(a.clone(), u.clone(), mask)
+    assert torch.allclose(ai.cpu(), g["a_imputed"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(af.cpu(), g["a_filtered"], rtol=1e-4, atol=1e-6)
+    assert torch.equal(ms2, outs[0]) and torch.equal(mf2, outs[2])
 
 
 def test_filter_step_and_smooth_step_match_reference_steps():
