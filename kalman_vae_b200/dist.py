@@ -77,20 +77,29 @@ class PeerExchange:
     def __init__(self, device, nfloats, group=None):
         from . import capi
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.comm, handle = capi.dp_create(device, self.rank, self.world, nfloats)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle, group=group)
-        ok, err = 1, ""
+        # every rank takes part in BOTH gathers whatever happens locally, so a failure on one rank cannot hang the others
+        self.comm, handle, ok, err = None, b"", 1, ""
         try:
-            capi.dp_connect(self.comm, handles)
-        except capi.KvaeError as e:   # e.g. no peer access between the devices
+            self.comm, handle = capi.dp_create(device, self.rank, self.world, nfloats)
+        except capi.KvaeError as e:
             ok, err = 0, str(e)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (ok, err, handle), group=group)
+        if all(o for o, _, _ in infos):
+            try:
+                capi.dp_connect(self.comm, [h for _, _, h in infos])
+            except capi.KvaeError as e:   # e.g. no peer access between the devices
+                ok, err = 0, str(e)
+        else:
+            ok = 0
+            err = err or "; ".join(e for o, e, _ in infos if not o)
         oks = [None] * self.world
         dist.all_gather_object(oks, (ok, err), group=group)
         if not all(o for o, _ in oks):
-            capi.dp_destroy(self.comm)
-            self.comm = None
-            raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(e for o, e in oks if not o))
+            if self.comm is not None:
+                capi.dp_destroy(self.comm)
+                self.comm = None
+            raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(sorted({e for o, e in oks if not o and e})))
 
     def close(self):
         from . import capi
