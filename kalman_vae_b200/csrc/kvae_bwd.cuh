@@ -103,9 +103,12 @@ template <class C> struct GradAcc {
       KV_UNROLL for (int r = 0; r < R; ++r) {
         float row[COLS];
         load_row<COLS>(basek + (k * N + row0 + r) * LD, row);
-        KV_UNROLL for (int j = 0; j < COLS; ++j) {
-          s = fmaf(Xb[r][j], row[j], s);
-          if constexpr (!DENSE) v[OFF + (k * R + r) * COLS + j] = fmaf(al[k], Xb[r][j], v[OFF + (k * R + r) * COLS + j]);
+        s = kv_dot<COLS>(Xb[r], row, s);
+        if constexpr (!DENSE) {
+          KV_UNROLL for (int j = 0; j + 1 < COLS; j += 2)
+            kv_fma2(v[OFF + (k * R + r) * COLS + j], v[OFF + (k * R + r) * COLS + j + 1], al[k], al[k], Xb[r][j], Xb[r][j + 1]);
+          if constexpr (COLS % 2 == 1)
+            v[OFF + (k * R + r) * COLS + COLS - 1] = fmaf(al[k], Xb[r][COLS - 1], v[OFF + (k * R + r) * COLS + COLS - 1]);
         }
       }
       dal[k] += s;

@@ -176,7 +176,7 @@ KV_FN void mix_one(const float* __restrict__ basek, int modes, const float (&al)
       KV_UNROLL for (int r = 0; r < C::R; ++r) {
         float row[COLS];
         load_row<COLS>(basek + (k * C::N + row0 + r) * LD, row);
-        KV_UNROLL for (int j = 0; j < COLS; ++j) out[r][j] = fmaf(al[k], row[j], out[r][j]);
+        kv_axpy<COLS>(al[k], row, out[r]);
       }
     }
   }
@@ -264,13 +264,92 @@ KV_FN bool gain(const Group<C::L, C::R>& g, const float* base, const float (&Sp)
 }
 
 // ---------------------------------------------------------------------------------------
+// One filter step (A.1) given the step's mixed matrices: shared by the lane-group sweep below and by the
+// thread-per-sequence kernel with staged streams (csrc/kvae_seq.cuh).
+// ---------------------------------------------------------------------------------------
+struct NoHook {
+  static constexpr bool ON = false;
+};
+template <class C> struct FilterStepOut {
+  float mup[C::R], muf[C::R];
+  float Sp[C::R][C::N], Sf[C::R][C::N];
+};
+template <class C, class Hook = NoHook>
+KV_FN bool filter_step_math(const Group<C::L, C::R>& g, const float* base, const FTiles<C>& tl, const StepIn<C>& cur,
+                            const float (&A)[C::R][C::N], const float (&Bm)[C::R][C::M], const float (&Ct)[C::R][C::P],
+                            const float (&Q)[C::R][C::N], const float (&Sig)[C::R][C::N], const float (&mu)[C::N],
+                            FilterStepOut<C>& o, Hook* hook = nullptr) {
+  constexpr int N = C::N, P = C::P, M = C::M, R = C::R, L = C::L;
+  constexpr bool MEM = C::MEM;
+  const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), CB = tl.np(0), KB = tl.np(1);
+  const int row0 = g.row0();
+  float (&mup)[R] = o.mup;
+  float (&muf)[R] = o.muf;
+  float (&Sp)[R][N] = o.Sp;
+  float (&Sf)[R][N] = o.Sf;
+  // predict (A.1): mu_p = A mu + B u ; Sigma_p = (A Sigma) A^T + Q        (kalman_filter.py:65-67)
+  KV_UNROLL for (int r = 0; r < R; ++r) {
+    float s1 = 0.f, s2 = 0.f;
+    KV_UNROLL for (int j = 0; j < N; ++j) s1 = fmaf(A[r][j], mu[j], s1);
+    KV_UNROLL for (int j = 0; j < M; ++j) s2 = fmaf(Bm[r][j], cur.u[j], s2);
+    mup[r] = s1 + s2;
+  }
+  {
+    auto Sf_v = publish<MEM, L, R, N>(g, Sig, X0);
+    float Mx[R][N];
+    mm_RS<false>(A, Sf_v, Mx);
+    auto A_v = publish<MEM, L, R, N>(g, A, X1);
+    mm_RSt<false>(Mx, A_v, Sp);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sp[r][j] += Q[r][j];
+  }
+  // update
+  auto Ct_v = publish<MEM, L, R, P>(g, Ct, CB);
+  GainOut<C> go;
+  const bool ok = gain<C>(g, base, Sp, mup, Ct, Ct_v, cur.y, cur.m, go);
+  if constexpr (Hook::ON) hook->after_gain(cur, go);
+  KV_UNROLL for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+    KV_UNROLL for (int q = 0; q < P; ++q) s = fmaf(go.Kg[r][q], go.r[q], s);
+    muf[r] = mup[r] + s;                                                     // :96
+  }
+  // Joseph form: Sigma_f = sym((G Sp) G^T + (K R) K^T), G = I - K C          (:99-101)
+  float G[R][N];
+  mm_RSt<false>(go.Kg, Ct_v, G);
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) G[r][j] = ((row0 + r == j) ? 1.0f : 0.0f) - G[r][j];
+  float Xm[R][N];
+  {
+    auto Sp_v = publish<MEM, L, R, N>(g, Sp, X2);
+    float T1[R][N];
+    mm_RS<false>(G, Sp_v, T1);
+    auto G_v = publish<MEM, L, R, N>(g, G, X1);
+    mm_RSt<false>(T1, G_v, Xm);
+    float KR[R][P];
+    const float* Rm = base + Base<C>::oR;
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int q = 0; q < P; ++q) {
+      float s = 0.f;
+      KV_UNROLL for (int q2 = 0; q2 < P; ++q2) s = fmaf(go.Kg[r][q2], Rm[q2 * P + q], s);
+      KR[r][q] = s;
+    }
+    auto K_v = publish<MEM, L, R, P>(g, go.Kg, KB);
+    float KRK[R][N];
+    mm_RSt<false>(KR, K_v, KRK);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] += KRK[r][j];
+  }
+  {
+    auto X_v = publish<MEM, L, R, N>(g, Xm, X0);
+    float Xt[R][N];
+    tr_rows<R, N>(X_v, row0, Xt);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sf[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
+  }
+
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------
 // sweep 1: filter.  On return Sig (own rows) and mu (replicated) hold the last filtered belief.
 // ---------------------------------------------------------------------------------------
 // Hook: compile-time extension points of the filter loop (csrc/kvae_lstm.cuh runs the LSTM dynamics network there);
 // NoHook compiles to nothing.
-struct NoHook {
-  static constexpr bool ON = false;
-};
 template <class C, class Hook = NoHook>
 KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, const Group<C::L, C::R>& g, int b, bool active,
                         float* stage_slot, float (&Sig)[C::R][C::N], float (&mu)[C::N], float (&mu_own)[C::R],
@@ -315,65 +394,13 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     // waits for the whole L2 round trip (measured: 40 % of the stall samples of this kernel before the reordering)
     if (staged && (t & 3) == 0 && t + 4 < T) ins.prefetch(a, g, bt + 4);
 
-    // predict (A.1): mu_p = A mu + B u ; Sigma_p = (A Sigma) A^T + Q        (kalman_filter.py:65-67)
-    float mup[R];
-    KV_UNROLL for (int r = 0; r < R; ++r) {
-      float s1 = 0.f, s2 = 0.f;
-      KV_UNROLL for (int j = 0; j < N; ++j) s1 = fmaf(A[r][j], mu[j], s1);
-      KV_UNROLL for (int j = 0; j < M; ++j) s2 = fmaf(Bm[r][j], cur.u[j], s2);
-      mup[r] = s1 + s2;
-    }
-    float Sp[R][N];
-    {
-      auto Sf_v = publish<MEM, L, R, N>(g, Sig, X0);
-      float Mx[R][N];
-      mm_RS<false>(A, Sf_v, Mx);
-      auto A_v = publish<MEM, L, R, N>(g, A, X1);
-      mm_RSt<false>(Mx, A_v, Sp);
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sp[r][j] += Q[r][j];
-    }
-    // update
-    auto Ct_v = publish<MEM, L, R, P>(g, Ct, CB);
-    GainOut<C> go;
+    FilterStepOut<C> fo;
     msum += cur.m;
-    ok = gain<C>(g, base, Sp, mup, Ct, Ct_v, cur.y, cur.m, go) && ok;
-    if constexpr (Hook::ON) hook->after_gain(cur, go);
-    float muf[R];
-    KV_UNROLL for (int r = 0; r < R; ++r) {
-      float s = 0.f;
-      KV_UNROLL for (int q = 0; q < P; ++q) s = fmaf(go.Kg[r][q], go.r[q], s);
-      muf[r] = mup[r] + s;                                                     // :96
-    }
-    // Joseph form: Sigma_f = sym((G Sp) G^T + (K R) K^T), G = I - K C          (:99-101)
-    float G[R][N];
-    mm_RSt<false>(go.Kg, Ct_v, G);
-    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) G[r][j] = ((row0 + r == j) ? 1.0f : 0.0f) - G[r][j];
-    float Xm[R][N];
-    {
-      auto Sp_v = publish<MEM, L, R, N>(g, Sp, X2);
-      float T1[R][N];
-      mm_RS<false>(G, Sp_v, T1);
-      auto G_v = publish<MEM, L, R, N>(g, G, X1);
-      mm_RSt<false>(T1, G_v, Xm);
-      float KR[R][P];
-      const float* Rm = base + Base<C>::oR;
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int q = 0; q < P; ++q) {
-        float s = 0.f;
-        KV_UNROLL for (int q2 = 0; q2 < P; ++q2) s = fmaf(go.Kg[r][q2], Rm[q2 * P + q], s);
-        KR[r][q] = s;
-      }
-      auto K_v = publish<MEM, L, R, P>(g, go.Kg, KB);
-      float KRK[R][N];
-      mm_RSt<false>(KR, K_v, KRK);
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] += KRK[r][j];
-    }
-    float Sf[R][N];
-    {
-      auto X_v = publish<MEM, L, R, N>(g, Xm, X0);
-      float Xt[R][N];
-      tr_rows<R, N>(X_v, row0, Xt);
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sf[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
-    }
+    ok = filter_step_math<C, Hook>(g, base, tl, cur, A, Bm, Ct, Q, Sig, mu, fo, hook) && ok;
+    const float (&mup)[R] = fo.mup;
+    const float (&muf)[R] = fo.muf;
+    const float (&Sp)[R][N] = fo.Sp;
+    const float (&Sf)[R][N] = fo.Sf;
 
     if (active) {
       KV_UNROLL for (int r = 0; r < R; ++r) {
@@ -443,6 +470,50 @@ template <class C> KV_FN void load_smooth_in(const Args& a, long bt, int row0, S
 }
 
 // ---------------------------------------------------------------------------------------
+// One RTS smoother step (A.2): Sig / mus enter as the smoothed belief at t+1 and leave as the one at t.  Shared by the
+// lane-group sweep below and the thread-per-sequence kernel (csrc/kvae_seq.cuh).
+// ---------------------------------------------------------------------------------------
+template <class C>
+KV_FN bool smoother_step_math(const Group<C::L, C::R>& g, const FTiles<C>& tl, const float (&Sf)[C::R][C::N],
+                              const float (&Sp1)[C::R][C::N], const float (&muf)[C::R], const float (&mup1)[C::R],
+                              const float (&A1)[C::R][C::N], float (&Sig)[C::R][C::N], float (&mus)[C::R]) {
+  constexpr int N = C::N, R = C::R, L = C::L;
+  constexpr bool MEM = C::MEM;
+  const TileRef X0 = tl.nn(0), X1 = tl.nn(1), X2 = tl.nn(2), VB = tl.vec(0);
+  const int row0 = g.row0();
+  float J[R][N], LU[R][N], invu[N];
+  const bool ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu);
+  // mu_s = mu_f + J (mu_s1 - mu_p1)                                            (:232)
+  float d_own[R], d[N];
+  KV_UNROLL for (int r = 0; r < R; ++r) d_own[r] = mus[r] - mup1[r];
+  allgather<MEM, L, R>(g, d_own, VB, d);
+  KV_UNROLL for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+    KV_UNROLL for (int j = 0; j < N; ++j) s = fmaf(J[r][j], d[j], s);
+    mus[r] = muf[r] + s;
+  }
+  // Sigma_s = sym(Sf + (J D) J^T), D = Sigma_s1 - Sp1                          (:234-235)
+  float D[R][N];
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) D[r][j] = Sig[r][j] - Sp1[r][j];
+  float Xm[R][N];
+  {
+    auto D_v = publish<MEM, L, R, N>(g, D, X2);
+    float T1[R][N];
+    mm_RS<false>(J, D_v, T1);
+    auto J_v = publish<MEM, L, R, N>(g, J, X0);
+    mm_RSt<false>(T1, J_v, Xm);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] = Sf[r][j] + Xm[r][j];
+  }
+  {
+    auto X_v = publish<MEM, L, R, N>(g, Xm, X1);
+    float Xt[R][N];
+    tr_rows<R, N>(X_v, row0, Xt);
+    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------
 // sweep 2: RTS smoother, t = T-2..0.  Sig / mus (own rows / entries) enter as the last filtered
 // belief (= smoothed belief at T-1).
 // ---------------------------------------------------------------------------------------
@@ -497,35 +568,7 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     //  mixing, so the first mixing FMA waited for the whole L2 round trip -- 40 % of this kernel's stall samples)
     if (staged && ((t + 1) & 3) == 0 && t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
     if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
-    float J[R][N], LU[R][N], invu[N];
-    ok = smoother_gain<C>(g, X0, X1, Sf, A1, Sp1, J, LU, invu) && ok;
-    // mu_s = mu_f + J (mu_s1 - mu_p1)                                            (:232)
-    float d_own[R], d[N];
-    KV_UNROLL for (int r = 0; r < R; ++r) d_own[r] = mus[r] - mup1[r];
-    allgather<MEM, L, R>(g, d_own, VB, d);
-    KV_UNROLL for (int r = 0; r < R; ++r) {
-      float s = 0.f;
-      KV_UNROLL for (int j = 0; j < N; ++j) s = fmaf(J[r][j], d[j], s);
-      mus[r] = muf[r] + s;
-    }
-    // Sigma_s = sym(Sf + (J D) J^T), D = Sigma_s1 - Sp1                          (:234-235)
-    float D[R][N];
-    KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) D[r][j] = Sig[r][j] - Sp1[r][j];
-    float Xm[R][N];
-    {
-      auto D_v = publish<MEM, L, R, N>(g, D, X2);
-      float T1[R][N];
-      mm_RS<false>(J, D_v, T1);
-      auto J_v = publish<MEM, L, R, N>(g, J, X0);
-      mm_RSt<false>(T1, J_v, Xm);
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Xm[r][j] = Sf[r][j] + Xm[r][j];
-    }
-    {
-      auto X_v = publish<MEM, L, R, N>(g, Xm, X1);
-      float Xt[R][N];
-      tr_rows<R, N>(X_v, row0, Xt);
-      KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = 0.5f * (Xm[r][j] + Xt[r][j]);
-    }
+    ok = smoother_step_math<C>(g, tl, Sf, Sp1, muf, mup1, A1, Sig, mus) && ok;
     if (active) {
       KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Sig[r]);
       store_row<R>(a.mu_s + bt * N + row0, mus);

@@ -55,6 +55,44 @@ struct alignas(16) f4 { float x, y, z, w; };
 struct alignas(8) f2 { float x, y; };
 
 // ---------------------------------------------------------------------------------------
+// Packed fp32 arithmetic (sm_100: fma.rn.f32x2 -> FFMA2, two IEEE fused multiply-adds per issue slot).
+// The kernels are instruction-issue bound, not FMA-pipe bound, so halving the FMA issue count pays directly.
+// ptxas folds the mov.b64 packs into register-pair operands (and a repeated scalar into a broadcast operand):
+// the SASS has no extra moves (profiles/r02_sass_opcodes.txt).  Host build (tests/hostsim): plain fmaf.
+//   (c0,c1) = (a0,a1) * (b0,b1) + (c0,c1)
+// ---------------------------------------------------------------------------------------
+KV_FN void kv_fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(rc));
+#else
+  c0 = fmaf(a0, b0, c0);
+  c1 = fmaf(a1, b1, c1);
+#endif
+}
+// c[j] += a * y[j], j = 0..NC-1 (pairs packed; identical rounding to the scalar loop)
+template <int NC> KV_FN void kv_axpy(float a, const float (&y)[NC], float (&c)[NC]) {
+  KV_UNROLL for (int j = 0; j + 1 < NC; j += 2) kv_fma2(c[j], c[j + 1], a, a, y[j], y[j + 1]);
+  if constexpr (NC % 2 == 1) c[NC - 1] = fmaf(a, y[NC - 1], c[NC - 1]);
+}
+// s + sum_k x[k] y[k]: even and odd k accumulate in the two halves of one packed register (s rides on the even half),
+// i.e. (s + x0 y0 + x2 y2 + ..) + (x1 y1 + x3 y3 + ..)
+template <int KD> KV_FN float kv_dot(const float (&x)[KD], const float (&y)[KD], float s) {
+  if constexpr (KD >= 4 && KD % 2 == 0) {
+    float s1 = 0.f;
+    KV_UNROLL for (int k = 0; k < KD; k += 2) kv_fma2(s, s1, x[k], x[k + 1], y[k], y[k + 1]);
+    return s + s1;
+  } else {
+    KV_UNROLL for (int k = 0; k < KD; ++k) s = fmaf(x[k], y[k], s);
+    return s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Static problem description.
 //   N,P,M,K : z_dim, a_dim, u_dim, number of mixture modes
 //   L       : lanes per sequence (divides N); R rows per lane
@@ -262,8 +300,7 @@ KV_FN void mm_RS(const float (&X)[R][KD], const V& Y, float (&C)[R][NC]) {
   KV_UNROLL for (int k = 0; k < KD; ++k) {
     float yr[NC];
     Y.row(k, yr);
-    KV_UNROLL for (int r = 0; r < R; ++r)
-      KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = fmaf(X[r][k], yr[j], C[r][j]);
+    KV_UNROLL for (int r = 0; r < R; ++r) kv_axpy<NC>(X[r][k], yr, C[r]);
   }
 }
 // C[r][j] (+)= sum_k X[r][k] * Y(j,k)
@@ -272,11 +309,7 @@ KV_FN void mm_RSt(const float (&X)[R][KD], const V& Y, float (&C)[R][NC]) {
   KV_UNROLL for (int j = 0; j < NC; ++j) {
     float yr[KD];
     Y.row(j, yr);
-    KV_UNROLL for (int r = 0; r < R; ++r) {
-      float s = ACC ? C[r][j] : 0.f;
-      KV_UNROLL for (int k = 0; k < KD; ++k) s = fmaf(X[r][k], yr[k], s);
-      C[r][j] = s;
-    }
+    KV_UNROLL for (int r = 0; r < R; ++r) C[r][j] = kv_dot<KD>(X[r], yr, ACC ? C[r][j] : 0.f);
   }
 }
 // C[r][j] (+)= sum_k Xv(k, row0+r) * Y(k,j)      (i.e. own rows of Xv^T * Y)
@@ -289,8 +322,7 @@ KV_FN void mm_StS(const VX& Xv, int row0, const VY& Y, float (&C)[R][NC]) {
     float yr[NC];
     Y.row(k, yr);
     KV_UNROLL for (int r = 0; r < R; ++r) {
-      const float xk = Xv.at(k, row0 + r);
-      KV_UNROLL for (int j = 0; j < NC; ++j) C[r][j] = fmaf(xk, yr[j], C[r][j]);
+      kv_axpy<NC>(Xv.at(k, row0 + r), yr, C[r]);
     }
   }
 }

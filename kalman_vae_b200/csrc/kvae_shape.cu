@@ -1,7 +1,7 @@
 // kvae_shape.cu — compiled once per shape with -DKV_N= -DKV_P= -DKV_M= -DKV_K= ; defines
 // ShapeOps<KV_N,KV_P,KV_M,KV_K> (lane-count and dynamics-variant dispatch).
 #include "kvae_ops.h"
-#include "kvae_kernels.cuh"
+#include "kvae_seq.cuh"
 
 namespace kvae {
 
@@ -38,7 +38,12 @@ BasePtrs make_base(const kvae_inputs& in) { return BasePtrs{in.A, in.Bm, in.C, i
 
 template <> bool ShapeOps<N, P, M, K>::lanes_ok(int lanes) { return KV_L_OK(lanes); }
 
+// thread-per-sequence kernels (csrc/kvae_seq.cuh): lanes == 1, z_dim = u_dim = 4, T % 4 == 0
+constexpr bool SEQ_SHAPE = (N == 4 && M == 4);
+static bool seq_dims_ok(const kvae_dims& d) { return SEQ_SHAPE && d.lanes == 1 && d.T % 4 == 0 && !(d.flags & KVAE_FLAG_SMOOTH_ONLY); }
+
 template <> int ShapeOps<N, P, M, K>::fwd_grid(const kvae_dims& d) {
+  if (seq_dims_ok(d)) return seq_grid(d.B);
 #define X(l) \
   if (d.lanes == (l)) { if constexpr (N % (l) == 0) return fwd_grid_of<Cfg<N, P, M, K, (l), false, false>>(d.B); }
   KV_FOR_EACH_L(X)
@@ -55,6 +60,12 @@ int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const k
   const BasePtrs bp = make_base(in);
   const int smooth = (st.mus_smooth != nullptr) ? 1 : 0;
   const bool sw = d.q_per_mode != 0;
+  if constexpr (SEQ_SHAPE) {
+    if (seq_dims_ok(d) && seq_eligible(a)) {
+      return sw ? launch_seq_fwd<Cfg<N, P, M, K, 1, true, true>>(a, bp, smooth, s)
+                : launch_seq_fwd<Cfg<N, P, M, K, 1, false, false>>(a, bp, smooth, s);
+    }
+  }
 #define X(l)                                                                                   \
   if (d.lanes == (l)) {                                                                        \
     if constexpr (N % (l) == 0) {                                                              \
