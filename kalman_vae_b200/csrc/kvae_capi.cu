@@ -19,11 +19,15 @@ struct DeviceGuard {
 };
 bool variant_ok(const kvae_dims& d) { return (d.q_per_mode != 0) == (d.c_shared != 0); }
 
-// lanes per sequence.  Measured on B200: for n <= 4 one row per lane (L = n) wins at EVERY batch size (cfg2: 44.7 us
-// vs 53.8 / 75.5 us for L = 2 / 1; cfg3 in full: 4.95 vs 3.67 G seq-steps/s for L = 1; the L = 1 backward kernel spills
-// 4 KB per thread), and for n = 16 L = 16 (fewer spills).  n = 8: smallest count that still gives >= 8 warps per SM.
+// lanes per sequence.  Measured on B200 (profiles/r02_*):
+//  * n = 4, u_dim = 4, T % 4 == 0 and at least 32 768 sequences: ONE lane, i.e. the thread-per-sequence kernels with
+//    TMA-staged streams (csrc/kvae_seq.cuh): B = 262 144, T = 20: forward 0.72 ms vs 0.84 ms, adjoint 1.93 vs 2.31 ms.
+//  * smaller batches are latency bound (a sequence is a chain of 4 T dependent steps): both families need ~2 000 cycles
+//    per step there; one row per lane (L = n) has more warps to overlap (cfg2, B = 8 192: adjoint 90 vs 130 us).
+//  * n = 16: L = 16 (fewer spills).  n = 8: smallest count that still gives >= 8 warps per SM.
 int pick_lanes(const kvae_dims& d) {
   const int n = d.n;
+  if (n == 4 && d.m == 4 && d.T % 4 == 0 && d.B >= 32768 && !(d.flags & KVAE_FLAG_SMOOTH_ONLY)) return 1;
   if (n <= 4) return n < 1 ? 1 : n;
   if (n != 8) return n;
   const long want_threads = 148L * 8 * 32;

@@ -15,9 +15,16 @@
 //   * the tiny per-step INPUT streams (y_t, u_t, alpha_t, mask_t, and dY / dalpha / dU going out): rows of 8 / 12 / 4
 //     bytes cannot be TMA boxes, so FOUR time steps travel together: tensor (T*W, B), box (4W, 32) -> [32][4W].
 //     Needs T % 4 == 0; other lengths run on the lane-group kernels.
-//   * loads are double buffered (mbarrier complete_tx, the next step / chunk in flight while this one is computed);
-//     stores leave from a single staging tile per warp (bulk_group; the next step waits for the tile to be READ, not
+//   * chunk loads complete on an mbarrier (complete_tx) and are re-armed one step before their first use; stores leave
+//     from a single staging tile per warp and stream (bulk_group; the next step waits for the tile to be READ, not
 //     for the write to land).
+//   * the TMA engine moves ~14-18 bytes per cycle and SM for such short rows (a 16-byte row costs ~2 cycles, a 64-byte
+//     row ~4.5; tools/microbench/ub_stream.cu), i.e. 4-5 TB/s for the whole chip: a kernel that pushes ALL its traffic
+//     through it is TMA-bound below the HBM roofline (measured: forward 2.3 TB/s algorithmic at 75 % TMA occupancy).
+//     So the two engines share the work: the 64-/32-byte rows and the input chunks use TMA, the 16-byte mean rows are
+//     stored with plain 128-bit stores, and the states a sweep READS BACK (smoother: Sigma_f(t), Sigma_p(t+1), ...)
+//     are fetched with ordinary vector loads one step ahead (each thread reads whole sectors of its own rows, which
+//     the LSU path sustains at 4.1 TB/s).
 //
 // Reference arithmetic: kvae/kalman/kalman_filter.py:31-279 (sweeps 1-2 here), :305-401 + autograd (sweeps 3-4,
 // csrc/kvae_seq_bwd.cuh).  The step arithmetic is the same code as the lane-group kernels (filter_step_math,
@@ -68,6 +75,47 @@ __device__ __forceinline__ void store3d(const CUtensorMap* m, int c0, int c1, in
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
+// L2 eviction-priority hints: streams that nobody reads again soon (A/B/C lists, smoothed states, final gradients) are
+// written evict_first so that they do not push the re-read streams (filtered / predicted states, adjoint scratch) out
+// of L2 between the sweep that writes them and the sweep that reads them back; last-use loads are evict_first too.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// (measured on B200, B = 262 144, T = 20: the hints cost 5 % in the forward kernel and change nothing in the adjoint:
+//  compiled in only with -DKV_SEQ_L2_HINTS=1)
+#ifndef KV_SEQ_L2_HINTS
+#define KV_SEQ_L2_HINTS 0
+#endif
+#if !KV_SEQ_L2_HINTS
+__device__ __forceinline__ void load2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar, uint64_t) { load2d(dst, m, c0, c1, bar); }
+__device__ __forceinline__ void load3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar, uint64_t) { load3d(dst, m, c0, c1, c2, bar); }
+__device__ __forceinline__ void store2d(const CUtensorMap* m, int c0, int c1, uint32_t src, uint64_t) { store2d(m, c0, c1, src); }
+__device__ __forceinline__ void store3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src, uint64_t) { store3d(m, c0, c1, c2, src); }
+#else
+__device__ __forceinline__ void load2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+               ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void load3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+               ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void store2d(const CUtensorMap* m, int c0, int c1, uint32_t src, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void store3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(src), "l"(pol) : "memory");
+}
+#endif
 __device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -114,51 +162,57 @@ template <int PIECES> struct RowTile {
 // tensor maps of the forward kernel (host: make_seq_fwd_maps)
 struct alignas(64) SeqFwdMaps {
   CUtensorMap Y, U, alpha, mask;                     // (T*W, B), box (4W, 32)
-  CUtensorMap mu_p, mu_f, mu_s;                      // (4, T, B), box (4, 1, 32)
   CUtensorMap Sig_p, Sig_f, Sig_s, A, B;             // (16, T, B), box (16, 1, 32), SWIZZLE_64B
   CUtensorMap C;                                     // (4P, T, B), box (4P, 1, 32), swizzle of a 16P-byte row
 };
 
 __host__ __device__ constexpr int kv_align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-// Shared-memory plan of one warp of k_seq_fwd (bytes; every tile 1024-byte aligned).  Sweep 2 reuses sweep 1's region.
+// Shared-memory plan of one warp of k_seq_fwd (bytes).  Swizzled tiles need their base aligned to the swizzle period
+// (512 bytes for SWIZZLE_64B, 256 for SWIZZLE_32B); every tile is 512-byte aligned.  Sweep 2 reuses sweep 1's region.
 template <class C> struct SeqFwdPlan {
-  static constexpr int P = C::P, K = C::K;
-  using TV = RowTile<1>;    // mu rows
+  static constexpr int P = C::P, K = C::K, M = C::M;
   using TM = RowTile<4>;    // Sigma / A / B rows
   using TC = RowTile<P>;    // C rows ([P][4])
-  // sweep 1: output tiles of one step, then the two input-chunk buffers
+  // output tiles of one step (sweep 2 reuses oSp for Sigma_s), then the input chunk (single buffer, re-armed one step
+  // ahead of its first use)
   static constexpr int oSp = 0, oSf = oSp + TM::bytes, oA = oSf + TM::bytes, oB = oA + TM::bytes;
   static constexpr int oC = oB + TM::bytes;
-  static constexpr int oMp = kv_align_up(oC + TC::bytes, 1024), oMf = oMp + 1024;
-  static constexpr int in_Y = 0, in_U = in_Y + 32 * 4 * P * 4, in_al = in_U + 32 * 16 * 4, in_m = in_al + 32 * 4 * K * 4;
-  static constexpr int in_bytes = kv_align_up(in_m + 32 * 4 * 4, 1024);
+  static constexpr int in_Y = 0, in_U = in_Y + 32 * 4 * P * 4, in_al = in_U + 32 * 4 * M * 4, in_m = in_al + 32 * 4 * K * 4;
+  static constexpr int in_bytes = kv_align_up(in_m + 32 * 4 * 4, 512);
   static __host__ __device__ constexpr uint32_t in_tx(bool has_u, bool has_m) {
-    return 32u * 4 * P * 4 + (has_u ? 32u * 16 * 4 : 0u) + 32u * 4 * K * 4 + (has_m ? 32u * 4 * 4 : 0u);
+    return 32u * 4 * P * 4 + (has_u ? 32u * 4 * M * 4 : 0u) + 32u * 4 * K * 4 + (has_m ? 32u * 4 * 4 : 0u);
   }
-  static constexpr int oIn0 = oMf + 1024, oIn1 = oIn0 + in_bytes;
-  static constexpr int sweep1 = oIn1 + in_bytes;
-  // sweep 2: two state buffers [Sigma_f(t) | Sigma_p(t+1) | mu_f(t) | mu_p(t+1)], the output tiles, two alpha chunks
-  static constexpr int st_Sf = 0, st_Sp = TM::bytes, st_mf = 2 * TM::bytes, st_mp = 2 * TM::bytes + 512;
-  static constexpr int st_bytes = 2 * TM::bytes + 1024;
-  static constexpr uint32_t st_tx = 2u * TM::bytes + 2u * TV::bytes;
-  static constexpr int oSt0 = 0, oSt1 = st_bytes, oSs = 2 * st_bytes, oMs = oSs + TM::bytes;
-  static constexpr int al_bytes = kv_align_up(32 * 4 * K * 4, 128);
-  static constexpr int oAl0 = oMs + 1024, oAl1 = oAl0 + al_bytes;
-  static constexpr int sweep2 = kv_align_up(oAl1 + al_bytes, 1024);
-  static constexpr int warp_bytes = sweep1 > sweep2 ? sweep1 : sweep2;
+  static constexpr int oIn = kv_align_up(oC + TC::bytes, 512);
+  static constexpr int warp_bytes = kv_align_up(oIn + in_bytes, 512);
 };
-
-template <class C> constexpr size_t seq_fwd_smem(int warps) {
-  return 1024 + (size_t)kv_align_up((int)sizeof(float) * Base<C>::total, 1024) + (size_t)warps * SeqFwdPlan<C>::warp_bytes;
-}
-// warps per CTA: small batches are spread over as many SMs as possible with two warps per CTA (distinct schedulers)
-inline int seq_warps_per_cta(int B) { return (B <= 148 * 64) ? 2 : 4; }
-inline int seq_grid(int B) { const int per = 32 * seq_warps_per_cta(B); return (B + per - 1) / per; }
 
 #ifndef KV_SEQ_MAXWARPS
 #define KV_SEQ_MAXWARPS 4
 #endif
+template <class C> constexpr size_t seq_fwd_smem(int warps) {
+  return 512 + (size_t)kv_align_up((int)sizeof(float) * Base<C>::total, 512) + (size_t)warps * SeqFwdPlan<C>::warp_bytes;
+}
+// warps per CTA.  A warp stages 14 KB; four-warp CTAs (three per SM by registers); small batches use two-warp CTAs so
+// that the few warps spread over all SMs and land on distinct schedulers.
+inline int seq_env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+inline int seq_warps_per_cta(int B) {
+  static const int forced = seq_env_int("KVAE_SEQ_FWD_WARPS", 0);   // development knob
+  if (forced >= 1 && forced <= KV_SEQ_MAXWARPS) return forced;
+  return ((B + 31) / 32 > 148 * 8) ? KV_SEQ_MAXWARPS : 2;
+}
+// Resident CTAs per SM are capped at TWO by requesting at least 100 KB of shared memory per CTA.  Measured on B200
+// (profiles/r02_seq_occupancy_sweep.log; B = 262 144, T = 20 and B = 32 768, T = 200): 8 warps per SM beat 12 in the forward
+// kernel (0.72 vs 0.83 ms: the smoother's read-back of the filter sweep's outputs finds more of them in L2) and 4 beat 6
+// in the adjoint (1.93 vs 2.31 ms: with three CTAs the unified L1/shared array has no L1 left for the adjoint's
+// register spills).  KVAE_SEQ_SMEM_FLOOR overrides the floor (development knob).
+inline size_t seq_smem_floor() { static const int v = seq_env_int("KVAE_SEQ_SMEM_FLOOR", 100 * 1024); return (size_t)v; }
+inline int seq_grid(int B) { const int per = 32 * seq_warps_per_cta(B); return (B + per - 1) / per; }
+
+struct SeqBar {   // mbarrier + the parity of its next completion
+  uint32_t addr, phase;
+  __device__ __forceinline__ void wait() { tma::bar_wait(addr, phase & 1u); ++phase; }
+};
 
 // step inputs from a staged 4-step chunk ([32][4W] rows, no swizzle)
 template <class C>
@@ -182,22 +236,21 @@ __device__ __forceinline__ void seq_read_step(const unsigned char* in, int lane,
 }
 
 template <class C>
-__global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePtrs bp, const __grid_constant__ SeqFwdMaps mp,
+__global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, BasePtrs bp, const __grid_constant__ SeqFwdMaps mp,
                                                                   int smooth) {
   static_assert(C::L == 1 && C::N == 4 && C::M == 4, "thread-per-sequence kernels: z_dim = u_dim = 4");
   constexpr int N = C::N, P = C::P, M = C::M, K = C::K, R = C::R;
   using PL = SeqFwdPlan<C>;
-  using TV = typename PL::TV;
   using TM = typename PL::TM;
   using TC = typename PL::TC;
   extern __shared__ unsigned char seq_smem_raw[];
   __shared__ __align__(8) unsigned long long bars[KV_SEQ_MAXWARPS][6];
   __shared__ float mred[KV_SEQ_MAXWARPS];
-  unsigned char* sm = seq_smem_raw + ((1024u - (tma::s32(seq_smem_raw) & 1023u)) & 1023u);
+  unsigned char* sm = seq_smem_raw + ((512u - (tma::s32(seq_smem_raw) & 511u)) & 511u);
   float* base = reinterpret_cast<float*>(sm);
   stage_base<C>(base, bp);   // __syncthreads inside
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wsm = sm + kv_align_up((int)sizeof(float) * Base<C>::total, 1024) + warp * PL::warp_bytes;
+  unsigned char* wsm = sm + kv_align_up((int)sizeof(float) * Base<C>::total, 512) + warp * PL::warp_bytes;
   const int b0 = blockIdx.x * blockDim.x + warp * 32;   // first sequence of this warp
   const int b = b0 + lane;
   const bool active = b < a.B;
@@ -206,9 +259,7 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePt
   const bool has_u = a.U != nullptr, has_m = a.mask != nullptr;
   const Group<1, R> g{0, 0xffffffffu};
   const FTiles<C> tl{base, 0};   // L = 1: never dereferenced (views alias registers)
-  const uint32_t bar_in0 = tma::s32(&bars[warp][0]), bar_in1 = tma::s32(&bars[warp][1]);
-  const uint32_t bar_st0 = tma::s32(&bars[warp][2]), bar_st1 = tma::s32(&bars[warp][3]);
-  const uint32_t bar_al0 = tma::s32(&bars[warp][4]), bar_al1 = tma::s32(&bars[warp][5]);
+  const uint32_t bar_in0 = tma::s32(&bars[warp][0]);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) tma::bar_init(tma::s32(&bars[warp][i]), 1);
@@ -219,20 +270,21 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePt
   float Sig[R][N], mu[N], mus[R];
   float msum = 0.f;
   bool ok = true;
+  const uint64_t pol_ef = tma::policy_evict_first(), pol_el = tma::policy_evict_last();
   if (warp_on) {
     // ------------------------------------------------------------------ sweep 1: filter
     copy_rows<C, N>(base + Base<C>::oS0, 0, Sig);
     load_row<N>(base + Base<C>::oMu0, mu);
     if (a.Sig_init && active) { KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_init + ((long)b * N + r) * N, Sig[r]); }
     if (a.mu_init && active) load_row<N>(a.mu_init + (long)b * N, mu);
-    auto issue_in = [&](int c) {   // lane 0: the four input streams of chunk c
-      unsigned char* buf = wsm + ((c & 1) ? PL::oIn1 : PL::oIn0);
-      const uint32_t bar = (c & 1) ? bar_in1 : bar_in0;
-      tma::bar_expect(bar, PL::in_tx(has_u, has_m));
-      tma::load2d(tma::s32(buf + PL::in_Y), &mp.Y, 4 * c * P, b0, bar);
-      if (has_u) tma::load2d(tma::s32(buf + PL::in_U), &mp.U, 4 * c * M, b0, bar);
-      tma::load2d(tma::s32(buf + PL::in_al), &mp.alpha, 4 * c * K, b0, bar);
-      if (has_m) tma::load2d(tma::s32(buf + PL::in_m), &mp.mask, 4 * c, b0, bar);
+    SeqBar bar_in{bar_in0, 0u};
+    unsigned char* ib = wsm + PL::oIn;
+    auto issue_in = [&](int c) {   // elected lane: the four input streams of chunk c
+      tma::bar_expect(bar_in.addr, PL::in_tx(has_u, has_m));
+      tma::load2d(tma::s32(ib + PL::in_Y), &mp.Y, 4 * c * P, b0, bar_in.addr, pol_ef);
+      if (has_u) tma::load2d(tma::s32(ib + PL::in_U), &mp.U, 4 * c * M, b0, bar_in.addr, pol_ef);
+      tma::load2d(tma::s32(ib + PL::in_al), &mp.alpha, 4 * c * K, b0, bar_in.addr, smooth ? pol_el : pol_ef);
+      if (has_m) tma::load2d(tma::s32(ib + PL::in_m), &mp.mask, 4 * c, b0, bar_in.addr, pol_ef);
     };
     if (tma::elect_one()) issue_in(0);
     float* tSp = reinterpret_cast<float*>(wsm + PL::oSp);
@@ -240,17 +292,21 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePt
     float* tA = reinterpret_cast<float*>(wsm + PL::oA);
     float* tB = reinterpret_cast<float*>(wsm + PL::oB);
     float* tC = reinterpret_cast<float*>(wsm + PL::oC);
-    float* tMp = reinterpret_cast<float*>(wsm + PL::oMp);
-    float* tMf = reinterpret_cast<float*>(wsm + PL::oMf);
-    for (int c = 0; c < nchunk; ++c) {
-      if (c + 1 < nchunk && tma::elect_one()) issue_in(c + 1);   // its buffer was released by the __syncwarp ending chunk c-1
-      tma::bar_wait((c & 1) ? bar_in1 : bar_in0, (uint32_t)((c >> 1) & 1));
-      const unsigned char* ib = wsm + ((c & 1) ? PL::oIn1 : PL::oIn0);
+    bar_in.wait();
+    StepIn<C> cur;
+    seq_read_step<C>(ib, lane, 0, has_u, has_m, cur);
 #pragma unroll 1
-      for (int s = 0; s < 4; ++s) {
-        const int t = 4 * c + s;
-        StepIn<C> cur;
-        seq_read_step<C>(ib, lane, s, has_u, has_m, cur);
+    for (int t = 0; t < T; ++t) {
+      {
+        // inputs of step t+1 (they become `cur` of the next iteration); the chunk buffer is re-armed with the next
+        // chunk as soon as its last step has been read, i.e. one whole step before that chunk's first use
+        StepIn<C> nxt = cur;
+        if (t + 1 < T) {
+          if (((t + 1) & 3) == 0) bar_in.wait();
+          seq_read_step<C>(ib, lane, (t + 1) & 3, has_u, has_m, nxt);
+        }
+        __syncwarp();
+        if (((t + 1) & 3) == 3 && t + 2 < T && tma::elect_one()) issue_in((t + 2) >> 2);
         float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
         mix_A<C>(base, cur.al, 0, A);
         mix_B<C>(base, cur.al, 0, Bm);
@@ -274,26 +330,26 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePt
         ok = filter_step_math<C>(g, base, tl, cur, A, Bm, Ct, Q, Sig, mu, fo) && ok;
         TM::st_mat(tSp, lane, fo.Sp);
         TM::st_mat(tSf, lane, fo.Sf);
-        TV::st(tMp, lane, 0, fo.mup);
-        TV::st(tMf, lane, 0, fo.muf);
+        if (active) {   // 16-byte rows: plain stores (see the file header)
+          store_row<N>(a.mu_p + ((long)b * T + t) * N, fo.mup);
+          store_row<N>(a.mu_f + ((long)b * T + t) * N, fo.muf);
+        }
         tma::fence_async();
         __syncwarp();
         if (tma::elect_one()) {
-          tma::store3d(&mp.Sig_p, 0, t, b0, tma::s32(tSp));
-          tma::store3d(&mp.Sig_f, 0, t, b0, tma::s32(tSf));
-          tma::store3d(&mp.mu_p, 0, t, b0, tma::s32(tMp));
-          tma::store3d(&mp.mu_f, 0, t, b0, tma::s32(tMf));
-          if (a.A_list) tma::store3d(&mp.A, 0, t, b0, tma::s32(tA));
-          if (a.B_list) tma::store3d(&mp.B, 0, t, b0, tma::s32(tB));
-          if (a.C_list) tma::store3d(&mp.C, 0, t, b0, tma::s32(tC));
+          tma::store3d(&mp.Sig_p, 0, t, b0, tma::s32(tSp), pol_el);   // read back by the smoother sweep
+          tma::store3d(&mp.Sig_f, 0, t, b0, tma::s32(tSf), pol_el);
+          if (a.A_list) tma::store3d(&mp.A, 0, t, b0, tma::s32(tA), pol_ef);
+          if (a.B_list) tma::store3d(&mp.B, 0, t, b0, tma::s32(tB), pol_ef);
+          if (a.C_list) tma::store3d(&mp.C, 0, t, b0, tma::s32(tC), pol_ef);
           tma::commit();
         }
         KV_UNROLL for (int r = 0; r < R; ++r) {
           KV_UNROLL for (int j = 0; j < N; ++j) Sig[r][j] = fo.Sf[r][j];
           mu[r] = fo.muf[r];
         }
+        cur = nxt;
       }
-      __syncwarp();   // every lane is done with input buffer c & 1
     }
     KV_UNROLL for (int r = 0; r < R; ++r) mus[r] = mu[r];
   }
@@ -311,78 +367,50 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS) k_seq_fwd(Args a, BasePt
   }
   if (warp_on && smooth) {
     // ------------------------------------------------------------------ sweep 2: RTS smoother, t = T-2 .. 0
-    // sweep 1's stores must have landed (the first step re-reads Sigma_f(T-2), Sigma_p(T-1)) and left the tiles
+    // sweep 1's TMA stores must have LANDED: the smoother reads Sigma_f / Sigma_p back with ordinary loads
     tma::wait_all0();
     __syncwarp();
-    float* tSs = reinterpret_cast<float*>(wsm + PL::oSs);
-    float* tMs = reinterpret_cast<float*>(wsm + PL::oMs);
-    auto issue_st = [&](int i) {   // lane 0: states of iteration i (t = T-2-i)
-      const int t = T - 2 - i;
-      unsigned char* buf = wsm + ((i & 1) ? PL::oSt1 : PL::oSt0);
-      const uint32_t bar = (i & 1) ? bar_st1 : bar_st0;
-      tma::bar_expect(bar, PL::st_tx);
-      tma::load3d(tma::s32(buf + PL::st_Sf), &mp.Sig_f, 0, t, b0, bar);
-      tma::load3d(tma::s32(buf + PL::st_Sp), &mp.Sig_p, 0, t + 1, b0, bar);
-      tma::load3d(tma::s32(buf + PL::st_mf), &mp.mu_f, 0, t, b0, bar);
-      tma::load3d(tma::s32(buf + PL::st_mp), &mp.mu_p, 0, t + 1, b0, bar);
-    };
-    auto issue_al = [&](int j) {   // lane 0: alpha chunk nchunk-1-j
-      const int c = nchunk - 1 - j;
-      const uint32_t bar = (j & 1) ? bar_al1 : bar_al0;
-      tma::bar_expect(bar, 32u * 4 * K * 4);
-      tma::load2d(tma::s32(wsm + ((j & 1) ? PL::oAl1 : PL::oAl0)), &mp.alpha, 4 * c * K, b0, bar);
-    };
-    if (tma::elect_one()) {
-      issue_al(0);
-      if (T >= 2) issue_st(0);
-    }
+    float* tSs = reinterpret_cast<float*>(wsm + PL::oSp);
+    const int bl = active ? b : a.B - 1;   // tail lanes re-read the last sequence and store nothing
     // t = T-1: copied, not symmetrised (kalman_filter.py:251-256)
     TM::st_mat(tSs, lane, Sig);
-    TV::st(tMs, lane, 0, mus);
+    if (active) store_row<N>(a.mu_s + ((long)b * T + (T - 1)) * N, mus);
     tma::fence_async();
     __syncwarp();
     if (tma::elect_one()) {
-      tma::store3d(&mp.Sig_s, 0, T - 1, b0, tma::s32(tSs));
-      tma::store3d(&mp.mu_s, 0, T - 1, b0, tma::s32(tMs));
+      tma::store3d(&mp.Sig_s, 0, T - 1, b0, tma::s32(tSs), pol_ef);
       tma::commit();
     }
-    int jal = 0;   // alpha chunk counter (0 = last chunk)
-    tma::bar_wait(bar_al0, 0u);
-    for (int i = 0; i + 2 <= T; ++i) {
-      const int t = T - 2 - i;
-      if (t > 0 && tma::elect_one()) issue_st(i + 1);          // buffer released by the __syncwarp ending iteration i-1
-      // alpha_{t+1}
-      const int c1 = (t + 1) >> 2;
-      if (nchunk - 1 - c1 != jal) {                     // (t+1) moved into the previous chunk
-        ++jal;
-        tma::bar_wait((jal & 1) ? bar_al1 : bar_al0, (uint32_t)((jal >> 1) & 1));
+    SmoothIn<C> pf;          // states of the NEXT iteration, fetched one step ahead
+    float al_pf[K];          // alpha_{t+1} of the next iteration
+    if (T >= 2) {
+      load_smooth_in<C>(a, (long)bl * T + (T - 2), 0, pf);
+      load_row<K>(a.alpha + ((long)bl * T + (T - 1)) * K, al_pf);
+    }
+#pragma unroll 1
+    for (int t = T - 2; t >= 0; --t) {
+      const long bt = (long)bl * T + t;
+      float Sf[R][N], Sp1[R][N], muf[R], mup1[R], al1[K];
+      KV_UNROLL for (int r = 0; r < R; ++r) {
+        KV_UNROLL for (int j = 0; j < N; ++j) { Sf[r][j] = pf.Sf[r][j]; Sp1[r][j] = pf.Sp1[r][j]; }
+        muf[r] = pf.muf[r]; mup1[r] = pf.mup1[r];
       }
-      if (((t + 1) & 3) == 3 && c1 > 0 && tma::elect_one()) issue_al(jal + 1);   // first use of chunk c1: fetch chunk c1-1
-      float al1[K];
-      {
-        const float* al = reinterpret_cast<const float*>(wsm + ((jal & 1) ? PL::oAl1 : PL::oAl0)) + lane * 4 * K + ((t + 1) & 3) * K;
-#pragma unroll
-        for (int k = 0; k < K; ++k) al1[k] = al[k];
-      }
+      KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = al_pf[k];
       float A1[R][N];
       mix_A<C>(base, al1, 0, A1);
-      tma::bar_wait((i & 1) ? bar_st1 : bar_st0, (uint32_t)((i >> 1) & 1));
-      const unsigned char* sb = wsm + ((i & 1) ? PL::oSt1 : PL::oSt0);
-      float Sf[R][N], Sp1[R][N], muf[R], mup1[R];
-      TM::ld_mat(reinterpret_cast<const float*>(sb + PL::st_Sf), lane, Sf);
-      TM::ld_mat(reinterpret_cast<const float*>(sb + PL::st_Sp), lane, Sp1);
-      TV::ld(reinterpret_cast<const float*>(sb + PL::st_mf), lane, 0, muf);
-      TV::ld(reinterpret_cast<const float*>(sb + PL::st_mp), lane, 0, mup1);
+      if (t > 0) {
+        load_smooth_in<C>(a, bt - 1, 0, pf);
+        load_row<K>(a.alpha + bt * K, al_pf);
+      }
       ok = smoother_step_math<C>(g, tl, Sf, Sp1, muf, mup1, A1, Sig, mus) && ok;
-      tma::wait_read0();   // all lanes: only the electing lane has groups pending
+      tma::wait_read0();
       __syncwarp();
       TM::st_mat(tSs, lane, Sig);
-      TV::st(tMs, lane, 0, mus);
+      if (active) store_row<N>(a.mu_s + ((long)b * T + t) * N, mus);
       tma::fence_async();
-      __syncwarp();   // also: every lane is done with state buffer i & 1 and (at a chunk change) the old alpha chunk
+      __syncwarp();
       if (tma::elect_one()) {
-        tma::store3d(&mp.Sig_s, 0, t, b0, tma::s32(tSs));
-        tma::store3d(&mp.mu_s, 0, t, b0, tma::s32(tMs));
+        tma::store3d(&mp.Sig_s, 0, t, b0, tma::s32(tSs), pol_ef);
         tma::commit();
       }
     }
@@ -445,16 +473,16 @@ template <class C> int launch_seq_fwd(const Args& a, const BasePtrs& bp, int smo
   bool okm = make_chunk_map(&mp.Y, a.Y, B, T, C::P) && make_chunk_map(&mp.alpha, a.alpha, B, T, C::K);
   if (a.U) okm = okm && make_chunk_map(&mp.U, a.U, B, T, C::M);
   if (a.mask) okm = okm && make_chunk_map(&mp.mask, a.mask, B, T, 1);
-  okm = okm && make_row_map(&mp.mu_p, a.mu_p, B, T, C::N) && make_row_map(&mp.mu_f, a.mu_f, B, T, C::N) &&
-        make_row_map(&mp.Sig_p, a.Sig_p, B, T, C::N * C::N) && make_row_map(&mp.Sig_f, a.Sig_f, B, T, C::N * C::N);
-  if (smooth) okm = okm && make_row_map(&mp.mu_s, a.mu_s, B, T, C::N) && make_row_map(&mp.Sig_s, a.Sig_s, B, T, C::N * C::N);
+  okm = okm && make_row_map(&mp.Sig_p, a.Sig_p, B, T, C::N * C::N) && make_row_map(&mp.Sig_f, a.Sig_f, B, T, C::N * C::N);
+  if (smooth) okm = okm && make_row_map(&mp.Sig_s, a.Sig_s, B, T, C::N * C::N);
   if (a.A_list) okm = okm && make_row_map(&mp.A, a.A_list, B, T, C::N * C::N);
   if (a.B_list) okm = okm && make_row_map(&mp.B, a.B_list, B, T, C::N * C::M);
   if (a.C_list) okm = okm && make_row_map(&mp.C, a.C_list, B, T, C::P * C::N);
   if (!okm) return -6;   // tensor-map encoding failed (driver entry point missing or misaligned pointer)
   const int warps = seq_warps_per_cta(B);
-  const size_t sm = seq_fwd_smem<C>(warps);
-  cudaError_t e = cudaFuncSetAttribute(k_seq_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_fwd_smem<C>(KV_SEQ_MAXWARPS));
+  size_t sm = seq_fwd_smem<C>(warps);
+  if (sm < seq_smem_floor()) sm = seq_smem_floor();
+  cudaError_t e = cudaFuncSetAttribute(k_seq_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return (int)e;
   k_seq_fwd<C><<<seq_grid(B), 32 * warps, sm, s>>>(a, bp, mp, smooth);
   return (int)cudaGetLastError();

@@ -1,7 +1,7 @@
 // kvae_shape.cu — compiled once per shape with -DKV_N= -DKV_P= -DKV_M= -DKV_K= ; defines
 // ShapeOps<KV_N,KV_P,KV_M,KV_K> (lane-count and dynamics-variant dispatch).
 #include "kvae_ops.h"
-#include "kvae_seq.cuh"
+#include "kvae_seq_bwd.cuh"
 
 namespace kvae {
 
@@ -126,11 +126,17 @@ int ShapeOps<N, P, M, K>::elbo(const kvae_dims& d, const kvae_inputs& in, const 
 
 template <> size_t ShapeOps<N, P, M, K>::bwd_ws(const kvae_dims& d) {
   const bool sw = d.q_per_mode != 0;
+  size_t seq_ws = 0;   // a lanes == 1 call may run on either kernel family (dense cotangents -> lane groups): take the larger
+  if constexpr (SEQ_SHAPE) {
+    if (seq_dims_ok(d)) seq_ws = sw ? seq_bwd_ws_bytes<Cfg<N, P, M, K, 1, true, true>>(d.B, d.T)
+                                    : seq_bwd_ws_bytes<Cfg<N, P, M, K, 1, false, false>>(d.B, d.T);
+  }
 #define X(l)                                                                                     \
   if (d.lanes == (l)) {                                                                          \
     if constexpr (N % (l) == 0) {                                                                \
-      return sw ? bwd_ws_bytes<Cfg<N, P, M, K, (l), true, true>>(d.B, d.T)                       \
-                : bwd_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B, d.T);                    \
+      const size_t lg = sw ? bwd_ws_bytes<Cfg<N, P, M, K, (l), true, true>>(d.B, d.T)           \
+                           : bwd_ws_bytes<Cfg<N, P, M, K, (l), false, false>>(d.B, d.T);        \
+      return lg > seq_ws ? lg : seq_ws;                                                          \
     }                                                                                            \
   }
   KV_FOR_EACH_L(X)
@@ -163,6 +169,12 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
   w.e_dSig = x.grads->dSigmas; w.e_dmu = x.grads->dmus;
   GradPtrs gp{x.grads->dA, x.grads->dBm, x.grads->dC, x.grads->dQ};
   const bool sw = d.q_per_mode != 0;
+  if constexpr (SEQ_SHAPE) {
+    if (seq_dims_ok(d) && seq_bwd_eligible(a, w, x.g_elbo)) {
+      return sw ? launch_seq_bwd<Cfg<N, P, M, K, 1, true, true>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s, x.dp)
+                : launch_seq_bwd<Cfg<N, P, M, K, 1, false, false>>(a, w, bp, x.g_elbo, x.terms, x.workspace, gp, s, x.dp);
+    }
+  }
 #define X(l)                                                                                             \
   if (d.lanes == (l)) {                                                                                  \
     if constexpr (N % (l) == 0) {                                                                        \

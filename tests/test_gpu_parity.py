@@ -127,3 +127,66 @@ def test_full_size_properties_cfg2():
     for k in ("dY", "dalpha", "dA"):
         a, b = res[1][2][k], res[4][2][k]
         assert float((a - b).norm() / b.norm()) < 1e-4, k
+
+
+def _elbo_only_case(name):
+    case = load_golden(name)[0]
+    return case
+
+
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_lstm_default", "kalman_switch", "kalman_fractional", "kalman_zero_mask"])
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_training_gradients_match_oracle(name, lanes):
+    """The training case proper: gradient of the ELBO alone (no cotangents on the smooth outputs) in the fused
+    value + adjoint launch.  With lanes = 1 and T % 4 == 0 this is the thread-per-sequence kernel pair
+    (csrc/kvae_seq.cuh, kvae_seq_bwd.cuh); the oracle (same op order as the reference, pinned by tests/test_oracle.py)
+    supplies fp32 and fp64 answers for exactly this loss."""
+    from oracle import kalman_oracle as ko
+    dev = torch.device("cuda:0")
+    case = _elbo_only_case(name)
+    r32 = ko.run_case(case, torch.float32, want_grads=True)
+    r64 = ko.run_case(case, torch.float64, want_grads=True)
+    pb, g = problem(case, lanes, dev)
+    F.info_word(dev).zero_()
+    st, *_ = F.smooth_fwd(pb)
+    t_f = torch.empty(8, device=dev)
+    gr = F.adjoint(pb, st, eps=g["eps"], g_elbo=torch.ones(1, device=dev), terms=t_f, with_elbo=True)
+    torch.cuda.synchronize()
+    assert int(F.info_word(dev)) == 0
+    check_close(f"{name}.L{lanes}.elbo", t_f[5], r32["elbo"], r64["elbo"])
+    gr = dict(dY=gr["dY"], dU=gr["dU"], dalpha=gr["dalpha"], dA=gr["dA"], dB=gr["dBm"], dC=gr["dC"], dQ=gr["dQ"])
+    for k in GRAD_NAMES:
+        if k in r32 and gr[k] is not None and float(r64[k].abs().max()) > 0:
+            e32, e64, floor = check_close(f"{name}.L{lanes}.{k}", gr[k], r32[k], r64[k])
+            print(f"{name}.L{lanes}.{k}: e32 {e32:.1e} e64 {e64:.1e} floor {floor:.1e}")
+
+
+def test_full_size_cfg2_against_oracle():
+    """BASELINE configs[1] at FULL size (B=8192, T=20): all nine outputs, the ELBO and the training gradients against
+    the CPU oracle in fp32 and fp64 (the oracle needs ~1 s for this size), default lane count."""
+    from kalman_vae_b200.synthetic import CONFIGS, make_case
+    from oracle import kalman_oracle as ko
+    dev = torch.device("cuda:0")
+    case = make_case(CONFIGS["cfg2"], seed=10)
+    r32 = ko.run_case(case, torch.float32, want_grads=True)
+    r64 = ko.run_case(case, torch.float64, want_grads=True)
+    pb, g = problem(case, 0, dev)
+    F.info_word(dev).zero_()
+    st, A_list, B_list, C_list = F.smooth_fwd(pb)
+    got = dict(mus_smooth=st.mus_smooth, Sigmas_smooth=st.Sigmas_smooth, mus_filt=st.mus_filt, Sigmas_filt=st.Sigmas_filt,
+               mus_pred=st.mus_pred, Sigmas_pred=st.Sigmas_pred, A_list=A_list, B_list=B_list, C_list=C_list)
+    worst = 0.0
+    for k in OUT_NAMES:
+        e32, e64, floor = check_close(f"cfg2.{k}", got[k], r32[k], r64[k])
+        worst = max(worst, e32)
+    t_f = torch.empty(8, device=dev)
+    gr = F.adjoint(pb, st, eps=g["eps"], g_elbo=torch.ones(1, device=dev), terms=t_f, with_elbo=True)
+    torch.cuda.synchronize()
+    assert int(F.info_word(dev)) == 0
+    check_close("cfg2.elbo", t_f[5], r32["elbo"], r64["elbo"])
+    gr = dict(dY=gr["dY"], dalpha=gr["dalpha"], dA=gr["dA"], dB=gr["dBm"], dC=gr["dC"])
+    for k, v in gr.items():
+        if float(r64[k].abs().max()) > 0:
+            e32, e64, floor = check_close(f"cfg2.{k}", v, r32[k], r64[k])
+            print(f"cfg2 full size {k}: e32 {e32:.1e} e64 {e64:.1e} floor {floor:.1e}")
+    print(f"cfg2 full size: worst forward error vs reference-order fp32 {worst:.1e}")
