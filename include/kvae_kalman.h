@@ -25,9 +25,12 @@
  *     another thread than forward).
  *   - return value: 0 ok; <0 invalid argument / unsupported shape (see kvae_last_error());
  *     >0 a cudaError_t raised by the launch.
- *   - `info` is a device int32 the kernels set to non-zero when a factorisation met a
- *     non-positive pivot (the reference would raise torch.linalg.LinAlgError or, in
- *     _safe_cholesky, retry with 10x jitter); the caller zeroes it and decides when to read it.
+ *   - `info` is a device int32 status word the kernels OR bits into; the caller zeroes it and decides when to
+ *     read it:  KVAE_INFO_PIVOT   a pivot of the filter / smoother / R / Sigma0 factorisations was not positive
+ *                                 (the reference raises torch.linalg.LinAlgError there),
+ *               KVAE_INFO_CHOL_S  chol(sym(Sigma_smooth) + jitter I) failed for some (b,t)      } _safe_cholesky
+ *               KVAE_INFO_CHOL_Q  chol(sym(Q_t) + jitter_q I) failed for some (b,t)              } would retry, 10x
+ *               KVAE_INFO_PEER    the data-parallel exchange gave up waiting for a peer (gradients not written).
  */
 #ifndef KVAE_KALMAN_H
 #define KVAE_KALMAN_H
@@ -39,11 +42,15 @@
 extern "C" {
 #endif
 
-#define KVAE_ABI_VERSION 5
+#define KVAE_ABI_VERSION 6
 #define KVAE_FLAG_SMOOTH_ONLY 1  /* kvae_dims.flags: forward entry skips the filter sweep (states given) */
 #define KVAE_FLAG_ELBO_ONLY 2    /* kvae_dims.flags: kvae_kf_bwd differentiates the ELBO alone, see kvae_grads */
 #define KVAE_FLAG_WITH_ELBO 4    /* kvae_dims.flags: kvae_kf_bwd also EVALUATES the ELBO (fused value + adjoint), see below */
 #define KVAE_FLAG_RAW_SUMS 8     /* with KVAE_FLAG_WITH_ELBO: leave every gradient un-normalised (data-parallel callers) */
+#define KVAE_INFO_PIVOT 1
+#define KVAE_INFO_PEER 2
+#define KVAE_INFO_CHOL_S 4
+#define KVAE_INFO_CHOL_Q 8
 
 typedef struct kvae_dims {
   int32_t B;          /* sequences in this call (the per-rank shard)               */
@@ -150,6 +157,23 @@ int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_state
                      const float* eps, float jitter, float* terms, void* workspace,
                      int32_t* info, int device, void* stream);
 
+/* The rungs of KalmanFilter._safe_cholesky (kalman_filter.py:282-302) beyond the first attempt.  The reference runs one
+ * ladder per call of _safe_cholesky, i.e. one for Sigma_smooth (:348) and an independent one for Q (:364-365): jitter
+ * 1e-6, 1e-5, .. 1e-2 for the WHOLE batch as soon as any matrix fails, then L = diag(sqrt(clamp(diag(sym(X)), 1e-6))).
+ * The kernels report which family failed (KVAE_INFO_CHOL_S / _Q); the caller re-launches with the next rung:
+ *   jitter (argument of the entry point) is added to sym(Sigma_smooth), jitter_q to sym(Q_t);
+ *   diag_smooth / diag_q != 0 select the diagonal fallback for that family (its jitter is then ignored); the adjoint
+ *   differentiates the fallback as autograd would (only unclamped diagonal entries carry gradient).
+ * NULL = { jitter_q = jitter, no fallback }: what kvae_kf_elbo_fwd / kvae_kf_bwd do. */
+typedef struct kvae_chol_opts {
+  float jitter_q;
+  int32_t diag_smooth;
+  int32_t diag_q;
+} kvae_chol_opts;
+int kvae_kf_elbo_fwd_ex(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                        const float* eps, float jitter, const kvae_chol_opts* opts, float* terms, void* workspace,
+                        int32_t* info, int device, void* stream);
+
 /* Cotangents of the nine `smooth` outputs (each may be NULL = zero). */
 typedef struct kvae_cotangents {
   const float* mus_smooth;    const float* Sigmas_smooth;
@@ -184,6 +208,12 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
                 const float* eps, float jitter, const float* g_elbo, float* terms,
                 const kvae_cotangents* cot, const kvae_grads* grads, void* workspace,
                 int32_t* info, int device, void* stream);
+
+/* kvae_kf_bwd with the _safe_cholesky rung given explicitly (see kvae_chol_opts) */
+int kvae_kf_bwd_ex(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st,
+                   const float* eps, float jitter, const kvae_chol_opts* opts, const float* g_elbo, float* terms,
+                   const kvae_cotangents* cot, const kvae_grads* grads, void* workspace,
+                   int32_t* info, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Data parallelism (one process per GPU, batch sharded): the single exchange of the training step, i.e. the

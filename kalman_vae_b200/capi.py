@@ -47,6 +47,13 @@ class KvaeLstm(Structure):
                [("hidden", c_int32)]
 
 
+class KvaeCholOpts(Structure):
+    _fields_ = [("jitter_q", c_float), ("diag_smooth", c_int32), ("diag_q", c_int32)]
+
+
+INFO_PIVOT, INFO_PEER, INFO_CHOL_S, INFO_CHOL_Q = 1, 2, 4, 8
+
+
 class KvaeError(RuntimeError):
     pass
 
@@ -76,6 +83,11 @@ def lib():
     L.kvae_kf_elbo_workspace_bytes.restype = c_size_t
     L.kvae_kf_elbo_fwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.kvae_kf_elbo_fwd_ex.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
+                                      POINTER(KvaeCholOpts), c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.kvae_kf_bwd_ex.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
+                                 POINTER(KvaeCholOpts), c_void_p, c_void_p, POINTER(KvaeCotangents), POINTER(KvaeGrads),
+                                 c_void_p, c_void_p, c_int, c_void_p]
     L.kvae_kf_bwd_workspace_bytes.argtypes = [POINTER(KvaeDims)]
     L.kvae_kf_bwd_workspace_bytes.restype = c_size_t
     L.kvae_kf_bwd.argtypes = [POINTER(KvaeDims), POINTER(KvaeInputs), POINTER(KvaeStates), c_void_p, c_float,
@@ -95,7 +107,7 @@ def lib():
     L.kvae_regime_sample_bwd.argtypes = [POINTER(KvaeRegimeDims)] + [c_void_p] * 10 + [c_int, c_void_p]
     L.kvae_kf_mask_partials_count.argtypes = [POINTER(KvaeDims)]
     L.kvae_kf_mask_partials_count.restype = c_size_t
-    if L.kvae_abi_version() != 5:
+    if L.kvae_abi_version() != 6:
         raise KvaeError("libkvae_kalman.so ABI version mismatch")
     _lib = L
     return L
@@ -104,7 +116,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "kvae_abi_version", "kvae_last_error", "kvae_supported", "kvae_pick_lanes",
     "kvae_kf_mask_partials_count", "kvae_kf_filter_smooth_fwd", "kvae_kf_filter_lstm_fwd", "kvae_kf_elbo_workspace_bytes", "kvae_kf_elbo_fwd",
-    "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd",
+    "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd", "kvae_kf_elbo_fwd_ex", "kvae_kf_bwd_ex",
     "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
     "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize", "kvae_kf_bwd_dp",
 ]
@@ -193,10 +205,21 @@ def elbo_workspace_bytes(dims) -> int:
     return int(lib().kvae_kf_elbo_workspace_bytes(byref(dims)))
 
 
+def _jit(jitter):
+    """jitter: a float (both factorisations, no fallback) or the rung of the reference's _safe_cholesky ladder as a
+    tuple (jitter_smooth, jitter_q, diag_smooth, diag_q) -> (float, KvaeCholOpts | None)"""
+    if isinstance(jitter, tuple):
+        js, jq, ds, dq = jitter
+        return float(js), KvaeCholOpts(float(jq), int(bool(ds)), int(bool(dq)))
+    return float(jitter), None
+
+
 def elbo_fwd(dims, inputs, states, eps, jitter, terms, workspace, info, device):
-    rc = lib().kvae_kf_elbo_fwd(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
-                                _ptr(terms, "terms"), c_void_p(workspace.data_ptr()), _ptr(info, "info"),
-                                device.index, _stream(device))
+    js, opts = _jit(jitter)
+    rc = lib().kvae_kf_elbo_fwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
+                                   byref(opts) if opts is not None else None,
+                                   _ptr(terms, "terms"), c_void_p(workspace.data_ptr()), _ptr(info, "info"),
+                                   device.index, _stream(device))
     _check(rc, "kvae_kf_elbo_fwd")
 
 
@@ -207,9 +230,11 @@ def bwd_workspace_bytes(dims) -> int:
 def bwd(dims, inputs, states, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device):
     cot_s = KvaeCotangents(*[_ptr(cot.get(k) if cot else None, "cot." + k) for k, _ in KvaeCotangents._fields_])
     grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
-    rc = lib().kvae_kf_bwd(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
-                           _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(cot_s), byref(grads_s),
-                           c_void_p(workspace.data_ptr()), _ptr(info, "info"), device.index, _stream(device))
+    js, opts = _jit(jitter)
+    rc = lib().kvae_kf_bwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
+                              byref(opts) if opts is not None else None,
+                              _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(cot_s), byref(grads_s),
+                              c_void_p(workspace.data_ptr()), _ptr(info, "info"), device.index, _stream(device))
     _check(rc, "kvae_kf_bwd")
 
 

@@ -225,10 +225,12 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
   const int T = a.T;
   const float c = w.c_elbo;
   const bool has_elbo = (c != 0.f);
-  bool ok = true;
+  bool ok = true, ok_s = true, ok_q = true;
+  const CholOpt co = chol_opt(a, w.jitter);
+  int bad0 = 0;
 
   ElboConst<C> ec;
-  if (has_elbo) ok = elbo_const<C>(g, base, T0, w.jitter, ec) && ok;
+  if (has_elbo) bad0 = elbo_const<C>(g, base, T0, co, ec);
   else {
     KV_UNROLL for (int q = 0; q < P; ++q) { ec.invdR[q] = 0.f; KV_UNROLL for (int q2 = 0; q2 < P; ++q2) ec.LR[q][q2] = 0.f; }
     KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) ec.LQ[r][j] = 0.f;
@@ -250,7 +252,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     if (has_elbo) {
       float eps0[N];
       load_row<N>(a.eps + bt0 * N, eps0);
-      ok = elbo_sample_t<C>(a, g, T0, VB, bt0, w.jitter, eps0, es) && ok;
+      ok_s = elbo_sample_t<C>(a, g, T0, VB, bt0, co, eps0, es) && ok_s;
     }
     // (Sigma_p, mu_p)-bar at t = 0 get no smoother contribution
     if (active) {
@@ -312,7 +314,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
       KV_UNROLL for (int r = 0; r < R; ++r) zbar_own[r] = xbar_own[r];
       float v_tr = 0.f, v_em = 0.f, v_in = 0.f, v_en = 0.f;   // this lane's share of the ELBO value terms of step t
       if (has_next) {
-        ok = elbo_sample_rows<C>(g, T0, VB, cu.Ss1, cu.ms1, w.jitter, cu.eps1, es1) && ok;
+        ok_s = elbo_sample_rows<C>(g, T0, VB, cu.Ss1, cu.ms1, co, cu.eps1, es1) && ok_s;
         // x_{t+1} = z_{t+1} - A1 z_t - B1 u_{t+1};  q = Qj^-1 x;  xbar = -c q
         float B1[R][M];
         mix_B<C>(base, al1, row0, B1);
@@ -328,8 +330,8 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
         if constexpr (C::QPM) {
           float Q1[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
           mix_Q<C>(base, al1, row0, Q1);
-          sym_jitter_rows<C>(g, Q1, T1, w.jitter, Qs);
-          ok = chol_dist<L, R>(g, Qs, LQ, invdQ, dgQ) && ok;
+          sym_jitter_rows<C>(g, Q1, T1, co.diag_q ? 0.f : co.jq, Qs);
+          ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
           auto LQ_v = publish<MEM, L, R, N>(g, LQ, T2);
           solve_vec_l<N>(x, LQ_v, invdQ);
           if (w.with_elbo) {   // log N(x; 0, Qj) = -1/2 (n log 2pi + |LQ^-1 x|^2) - sum log diag LQ   (own-lane log terms)
@@ -344,8 +346,11 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
           KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Qi[r][j] = (row0 + r == j) ? 1.f : 0.f;
           solve_rows_llt<R, N>(Qi, LQ_v, invdQ);
           pick_own<C>(g, x, q_own);
-          KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j)
-            Qb[r][j] += 0.5f * c * (q_own[r] * x[j] - Qi[r][j]);
+          KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
+            // diagonal fallback: only the unclamped diagonal entries of sym(Q_t) reach L (kalman_filter.py:298-302)
+            const bool live = !co.diag_q || (row0 + r == j && dgQ[r] * dgQ[r] > 1e-6f);
+            Qb[r][j] += live ? 0.5f * c * (q_own[r] * x[j] - Qi[r][j]) : 0.f;
+          }
         } else {
           solve_vec_l<N>(x, LQc_v, ec.invdQ);
           if (w.with_elbo && g.lane == 0) {
@@ -445,7 +450,9 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
         KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
           const int i = row0 + r;
           const float ve = v_own[r] * eps[j];
-          Phi[r][j] = (j < i) ? ve : ((j == i) ? 0.5f * (ve + c) : 0.f);
+          // (diagonal fallback: L depends on the unclamped diagonal entries of sym(Sigma_s) only)
+          const bool live_d = !co.diag_s || es.dg[r] * es.dg[r] > 1e-6f;
+          Phi[r][j] = (j < i) ? (co.diag_s ? 0.f : ve) : ((j == i && live_d) ? 0.5f * (ve + c) : 0.f);
         }
         solve_rows_l<R, N>(Phi, Ls_v, es.invd);                       // Z = Phi Ls^-1
         float Zt[R][N];
@@ -581,7 +588,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
     if (has_elbo && has_next) es = es1;
     KV_UNROLL for (int j = 0; j < N; ++j) eps_cur[j] = cu.eps1[j];
   }
-  if (!ok && active) *a.info = 1;
+  if (active) kv_info_or(a.info, bad0 | (ok ? 0 : KV_INFO_PIVOT) | (ok_s ? 0 : KV_INFO_CHOL_S) | (ok_q ? 0 : KV_INFO_CHOL_Q));
 }
 
 // What sweep 4 reads from global memory for step t (prefetched one step ahead, as in sweep 3)
@@ -839,7 +846,7 @@ KV_FN void bwd_sweep4(const Args& a, const BwdArgs& w, const float* base, const 
       }
     }
   }
-  if (!ok && active) *a.info = 1;
+  if (!ok && active) kv_info_or(a.info, KV_INFO_PIVOT);
 }
 
 }  // namespace kvae

@@ -138,6 +138,13 @@ size_t kvae_kf_elbo_workspace_bytes(const kvae_dims* d) {
 
 int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
                      float* terms, void* workspace, int32_t* info, int device, void* stream) {
+  return kvae_kf_elbo_fwd_ex(d, in, st, eps, jitter, nullptr, terms, workspace, info, device, stream);
+}
+
+int kvae_kf_elbo_fwd_ex(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                        const kvae_chol_opts* opts, float* terms, void* workspace, int32_t* info, int device, void* stream) {
+  const float jitter_q = opts ? opts->jitter_q : jitter;
+  const int chol_diag = opts ? ((opts->diag_smooth ? 1 : 0) | (opts->diag_q ? 2 : 0)) : 0;
   kvae_dims dd;
   if (int rc = check_common(d, in, st, &dd)) return rc;
   if (!info || !eps || !terms || !workspace) return fail(-1, "null argument");
@@ -146,7 +153,7 @@ int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_state
   DeviceGuard guard(device);
 #define X(n_, p_, m_, k_)                                                                                   \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
-    int rc = kvae::ShapeOps<n_, p_, m_, k_>::elbo(dd, *in, *st, eps, jitter, terms, workspace, info, (cudaStream_t)stream); \
+    int rc = kvae::ShapeOps<n_, p_, m_, k_>::elbo(dd, *in, *st, eps, jitter, jitter_q, chol_diag, terms, workspace, info, (cudaStream_t)stream); \
     if (rc > 0) return fail(rc, cudaGetErrorString((cudaError_t)rc));                                       \
     if (rc < 0) return fail(rc, "elbo launch rejected");                                                    \
     return 0;                                                                                               \
@@ -156,20 +163,35 @@ int kvae_kf_elbo_fwd(const kvae_dims* d, const kvae_inputs* in, const kvae_state
   return fail(-2, "unsupported shape");
 }
 
-size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d) {
-  if (!d) return 0;
-  kvae_dims dd = *d;
-  if (dd.lanes == 0) dd.lanes = pick_lanes(dd);
+static size_t bwd_ws_for(const kvae_dims& dd) {
 #define X(n_, p_, m_, k_) \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) return kvae::ShapeOps<n_, p_, m_, k_>::bwd_ws(dd);
   KVAE_FOR_EACH_SHAPE(X)
 #undef X
   return 0;
 }
+size_t kvae_kf_bwd_workspace_bytes(const kvae_dims* d) {
+  if (!d) return 0;
+  kvae_dims dd = *d;
+  if (dd.lanes != 0) return bwd_ws_for(dd);
+  // library-picked lanes: a call with dense cotangents runs on the lane-group kernels even where the thread-per-sequence
+  // kernels are the default (see bwd_impl), so the workspace covers both
+  dd.lanes = pick_lanes(dd);
+  size_t ws = bwd_ws_for(dd);
+  if (dd.lanes == 1 && dd.n > 1) {
+    dd.lanes = dd.n;
+    const size_t w2 = bwd_ws_for(dd);
+    if (w2 > ws) ws = w2;
+  }
+  return ws;
+}
 
 static int bwd_impl(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
                     const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
-                    void* workspace, int32_t* info, int device, void* stream, kvae_dp_comm* comm) {
+                    void* workspace, int32_t* info, int device, void* stream, kvae_dp_comm* comm,
+                    const kvae_chol_opts* opts = nullptr) {
+  const float jitter_q = opts ? opts->jitter_q : jitter;
+  const int chol_diag = opts ? ((opts->diag_smooth ? 1 : 0) | (opts->diag_q ? 2 : 0)) : 0;
   kvae_dims dd;
   if (int rc = check_common(d, in, st, &dd)) return rc;
   if (!info || !grads || !workspace) return fail(-1, "null argument");
@@ -189,6 +211,11 @@ static int bwd_impl(const kvae_dims* d, const kvae_inputs* in, const kvae_states
   } else if (dd.flags & KVAE_FLAG_RAW_SUMS) {
     return fail(-2, "RAW_SUMS without WITH_ELBO");
   }
+  {   // dense cotangents are not covered by the thread-per-sequence adjoint: with library-picked lanes use lane groups
+    const bool any_cot = cot && (cot->mus_smooth || cot->Sigmas_smooth || cot->mus_filt || cot->Sigmas_filt || cot->mus_pred ||
+                                 cot->Sigmas_pred || cot->A_list || cot->B_list || cot->C_list);
+    if (d->lanes == 0 && dd.lanes == 1 && dd.n > 1 && (any_cot || (dd.flags & KVAE_FLAG_ELBO_ONLY))) dd.lanes = dd.n;
+  }
   kvae::DpView view;
   if (comm) {
     if ((dd.flags & (KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS)) != (KVAE_FLAG_WITH_ELBO | KVAE_FLAG_RAW_SUMS) ||
@@ -197,7 +224,7 @@ static int bwd_impl(const kvae_dims* d, const kvae_inputs* in, const kvae_states
     if (!kvae::kvae_dp_get_view(comm, &view)) return fail(-1, "kvae_kf_bwd_dp: communicator not connected");
   }
   DeviceGuard guard(device);
-  kvae::BwdExtra x{eps, jitter, g_elbo, terms, cot, grads, workspace, comm ? &view : nullptr};
+  kvae::BwdExtra x{eps, jitter, jitter_q, chol_diag, g_elbo, terms, cot, grads, workspace, comm ? &view : nullptr};
 #define X(n_, p_, m_, k_)                                                                                   \
   if (dd.n == n_ && dd.p == p_ && dd.m == m_ && dd.K == k_) {                                              \
     int rc = kvae::ShapeOps<n_, p_, m_, k_>::bwd(dd, *in, *st, x, info, (cudaStream_t)stream);             \
@@ -214,6 +241,12 @@ int kvae_kf_bwd(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st
                 const float* g_elbo, float* terms, const kvae_cotangents* cot, const kvae_grads* grads,
                 void* workspace, int32_t* info, int device, void* stream) {
   return bwd_impl(d, in, st, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device, stream, nullptr);
+}
+
+int kvae_kf_bwd_ex(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,
+                   const kvae_chol_opts* opts, const float* g_elbo, float* terms, const kvae_cotangents* cot,
+                   const kvae_grads* grads, void* workspace, int32_t* info, int device, void* stream) {
+  return bwd_impl(d, in, st, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device, stream, nullptr, opts);
 }
 
 int kvae_kf_bwd_dp(const kvae_dims* d, const kvae_inputs* in, const kvae_states* st, const float* eps, float jitter,

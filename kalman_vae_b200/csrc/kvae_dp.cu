@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k_dp_final(DpPeers peers, int rank, int w
     part[q][j] = v;
   }
   __syncthreads();
-  if (bad) { if (threadIdx.x == 0) *info = 2; return; }
+  if (bad) { if (threadIdx.x == 0) atomicOr(info, 2); return; }
   if (threadIdx.x < 5) {
     double v = 0.0;
     for (int r = 0; r < world; ++r) v += (double)part[r][threadIdx.x];   // rank order, fp64
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) k_dp_final(DpPeers peers, int rank, int w
       ok = ld_ll(mine + ll_off(s, world, r, nf_pad, i), step, x) && ok;
       v += (double)x;
     }
-    if (!ok) { *info = 2; return; }
+    if (!ok) { atomicOr(info, 2); return; }
     const float f = (float)v * scale;
     int o = i;
 #pragma unroll

@@ -27,29 +27,39 @@ template <class C> KV_FN float logdet_half(const Group<C::L, C::R>& g, const flo
   return g.allreduce1(s);
 }
 
+// jitters and fallback switches of the two ELBO factorisations (see Args::jitter_q / chol_diag)
+struct CholOpt {
+  float js, jq;
+  int diag_s, diag_q;
+};
+KV_FN CholOpt chol_opt(const Args& a, float jitter_s) {
+  return CholOpt{jitter_s, a.jitter_q, a.chol_diag & 1, (a.chol_diag >> 1) & 1};
+}
+
 // constants of the ELBO that do not depend on t
 template <class C> struct ElboConst {
   float LR[C::P][C::P], invdR[C::P], logdetR;          // chol(R)                         (:373)
   float LQ[C::R][C::N], invdQ[C::N], logdetQ;          // chol(sym(Q)+jitter I), fixed Q  (:364-365)
 };
 
+// returns the status bits of what failed (0 = fine): chol(R) -> KV_INFO_PIVOT, chol(sym(Q)+jitter) -> KV_INFO_CHOL_Q
 template <class C>
-KV_FN bool elbo_const(const Group<C::L, C::R>& g, const float* base, TileRef xbuf, float jitter, ElboConst<C>& ec) {
+KV_FN int elbo_const(const Group<C::L, C::R>& g, const float* base, TileRef xbuf, const CholOpt& co, ElboConst<C>& ec) {
   constexpr int N = C::N, P = C::P, R = C::R;
-  bool ok = true;
+  int bad = 0;
   float Rm[P][P];
   KV_UNROLL for (int a = 0; a < P; ++a) KV_UNROLL for (int b = 0; b < P; ++b) Rm[a][b] = base[Base<C>::oR + a * P + b];
-  ok = chol_small<P>(Rm, ec.LR, ec.invdR) && ok;
+  if (!chol_small<P>(Rm, ec.LR, ec.invdR)) bad |= KV_INFO_PIVOT;
   ec.logdetR = 0.f;
   KV_UNROLL for (int a = 0; a < P; ++a) ec.logdetR += logf(ec.LR[a][a]);
   if constexpr (!C::QPM) {
     float Q[R][N], Qs[R][N], dg[R];
     copy_rows<C, N, Base<C>::ldQ>(base + Base<C>::oQ, g.row0(), Q);
-    sym_jitter_rows<C>(g, Q, xbuf, jitter, Qs);
-    ok = chol_dist<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg) && ok;
+    sym_jitter_rows<C>(g, Q, xbuf, co.diag_q ? 0.f : co.jq, Qs);
+    if (!chol_dist_opt<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg, co.diag_q)) bad |= KV_INFO_CHOL_Q;
     ec.logdetQ = logdet_half<C>(g, dg);
   }
-  return ok;
+  return bad;
 }
 
 // Per-step pieces of the ELBO that the adjoint recomputes as well.
@@ -64,11 +74,11 @@ template <class C> struct ElboStep {
 // z_t from the lane's rows of Sigma_s and entries of mu_s (xbuf: [N x N] tile, vbuf: N-vector slot)
 template <class C>
 KV_FN bool elbo_sample_rows(const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, const float (&Ss)[C::R][C::N],
-                            const float (&mus)[C::R], float jitter, const float (&eps)[C::N], ElboStep<C>& es) {
+                            const float (&mus)[C::R], const CholOpt& co, const float (&eps)[C::N], ElboStep<C>& es) {
   constexpr int N = C::N, R = C::R;
   float Sj[R][N];
-  sym_jitter_rows<C>(g, Ss, xbuf, jitter, Sj);                         // (:287, :293)
-  const bool ok = chol_dist<C::L, R>(g, Sj, es.Ls, es.invd, es.dg);
+  sym_jitter_rows<C>(g, Ss, xbuf, co.diag_s ? 0.f : co.js, Sj);        // (:287, :293)
+  const bool ok = chol_dist_opt<C::L, R>(g, Sj, es.Ls, es.invd, es.dg, co.diag_s);
   KV_UNROLL for (int r = 0; r < R; ++r) {
     float s = 0.f;
     KV_UNROLL for (int q = 0; q < N; ++q) s = fmaf(es.Ls[r][q], eps[q], s);
@@ -79,14 +89,14 @@ KV_FN bool elbo_sample_rows(const Group<C::L, C::R>& g, TileRef xbuf, TileRef vb
 }
 // same, loading Sigma_s / mu_s at index bt
 template <class C>
-KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, long bt, float jitter,
+KV_FN bool elbo_sample_t(const Args& a, const Group<C::L, C::R>& g, TileRef xbuf, TileRef vbuf, long bt, const CholOpt& co,
                          const float (&eps)[C::N], ElboStep<C>& es) {
   constexpr int N = C::N, R = C::R;
   const int row0 = g.row0();
   float Ss[R][N], mus[R];
   KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Ss[r]);
   load_row<R>(a.mu_s + bt * N + row0, mus);
-  return elbo_sample_rows<C>(g, xbuf, vbuf, Ss, mus, jitter, eps, es);
+  return elbo_sample_rows<C>(g, xbuf, vbuf, Ss, mus, co, eps, es);
 }
 
 // ELBO terms of time steps [t0, t1) of sequence b (the steps are independent given z_{t0-1}, which is
@@ -100,8 +110,10 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
   constexpr bool MEM = C::MEM;
   const int row0 = g.row0();
   const int T = a.T;
+  const CholOpt co = chol_opt(a, jitter);
   ElboConst<C> ec;
-  bool ok = elbo_const<C>(g, base, tl.nn(0), jitter, ec);
+  int bad = elbo_const<C>(g, base, tl.nn(0), co, ec);
+  bool ok = true, ok_s = true, ok_q = true;
   typename view_of<MEM, L, R, N>::type LQc_v = publish<MEM, L, R, N>(g, ec.LQ, tl.nn(3));
   float zprev[N];
   KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = 0.f;
@@ -111,7 +123,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
     float epsp[N];
     load_row<N>(a.eps + btp * N, epsp);
     ElboStep<C> esp;
-    ok = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), btp, jitter, epsp, esp) && ok;
+    ok_s = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), btp, co, epsp, esp) && ok_s;
     KV_UNROLL for (int j = 0; j < N; ++j) zprev[j] = esp.z[j];
   }
 
@@ -122,7 +134,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
     float eps[N];
     load_row<N>(a.eps + bt * N, eps);
     ElboStep<C> es;
-    ok = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), bt, jitter, eps, es) && ok;
+    ok_s = elbo_sample_t<C>(a, g, tl.nn(0), tl.vec(0), bt, co, eps, es) && ok_s;
     if (zbuf && active) store_row<R>(zbuf + bt * N + row0, es.z_own);
 
     // entropy = -log N(z; mu_s, Ls Ls^T) = 1/2 |eps|^2 + sum log Ls_ii + n/2 log 2pi            (:389)
@@ -159,8 +171,8 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
       if constexpr (C::QPM) {
         float Q[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
         mix_Q<C>(base, in.al, row0, Q);
-        sym_jitter_rows<C>(g, Q, tl.nn(1), jitter, Qs);
-        ok = chol_dist<L, R>(g, Qs, LQ, invdQ, dgQ) && ok;
+        sym_jitter_rows<C>(g, Q, tl.nn(1), co.diag_q ? 0.f : co.jq, Qs);
+        ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
         auto LQ_v = publish<MEM, L, R, N>(g, LQ, tl.nn(2));
         solve_vec_l<N>(x, LQ_v, invdQ);
         ld = logdet_half<C>(g, dgQ);
@@ -195,7 +207,7 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
   if (active && g.lane == 0) {
     acc[0] += s_tr; acc[1] += s_em; acc[2] += s_in; acc[3] += s_en; acc[4] += s_m;
   }
-  if (!ok && active) *a.info = 1;
+  if (active) kv_info_or(a.info, bad | (ok ? 0 : KV_INFO_PIVOT) | (ok_s ? 0 : KV_INFO_CHOL_S) | (ok_q ? 0 : KV_INFO_CHOL_Q));
 }
 
 }  // namespace kvae

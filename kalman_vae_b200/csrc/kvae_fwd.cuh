@@ -37,8 +37,26 @@ struct Args {
   const float* dQ;   // [B,T,N,N]  nullable -> base Q
   int smooth_only;   // 1: skip the filter sweep, smooth from the filtered states already in mu_f / Sig_f
   float* mask_part;  // optional out (forward kernel): per-CTA sum of the mask, see kvae_states.mask_partials
-  int* info;  // device word, set to nonzero if a Cholesky pivot was not positive
+  // ELBO factorisations (kalman_filter.py:282-302 _safe_cholesky): jitter added to sym(Q_t) (the one added to sym(Sigma_s)
+  // travels with the ELBO / adjoint calls) and the final rung of the reference's ladder, L = diag(sqrt(clamp(diag, 1e-6))),
+  // selected per matrix family: bit 0 = Sigma_smooth, bit 1 = Q
+  float jitter_q;
+  int chol_diag;
+  int* info;  // device status word, OR of KV_INFO_* bits
 };
+// status bits: a pivot of the filter / smoother / R / Sigma_0 factorisations was not positive (the reference raises
+// LinAlgError); the Cholesky of sym(Sigma_smooth)+jitter / sym(Q_t)+jitter failed (the reference retries with 10x jitter);
+// 2 is the data-parallel exchange time-out (kvae_kernels.cuh)
+#define KV_INFO_PIVOT 1
+#define KV_INFO_CHOL_S 4
+#define KV_INFO_CHOL_Q 8
+KV_FN void kv_info_or(int* info, int code) {
+#if defined(__CUDA_ARCH__)
+  if (code) atomicOr(info, code);
+#else
+  if (code) *info |= code;
+#endif
+}
 
 constexpr int pad4(int x) { return (x + 3) & ~3; }
 
@@ -434,7 +452,7 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     }
   }
   if (msum_out) *msum_out = msum;
-  if (!ok && active) *a.info = 1;
+  if (!ok && active) kv_info_or(a.info, KV_INFO_PIVOT);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -574,7 +592,7 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       store_row<R>(a.mu_s + bt * N + row0, mus);
     }
   }
-  if (!ok && active) *a.info = 1;
+  if (!ok && active) kv_info_or(a.info, KV_INFO_PIVOT);
 }
 
 }  // namespace kvae

@@ -538,7 +538,7 @@ static __global__ void __launch_bounds__(128) k_bwd_final_dp(const float* __rest
   const double nrm = tot[4] < 1.0 ? 1.0 : tot[4];
   const float scale = (float)(1.0 / nrm);
   if (bad) {
-    if (threadIdx.x == 0) *info = 2;
+    if (threadIdx.x == 0) atomicOr(info, 2);
   } else {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       for (int j = 0; j < 5; ++j) terms[j] = (float)tot[j];

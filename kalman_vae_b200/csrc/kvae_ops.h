@@ -18,7 +18,7 @@ constexpr int KV_DP_HDR_WORDS = 16;
 bool kvae_dp_get_view(kvae_dp_comm* c, DpView* out);   // false if the communicator is not connected
 
 struct BwdExtra {
-  const float* eps; float jitter; const float* g_elbo; float* terms;
+  const float* eps; float jitter; float jitter_q; int chol_diag; const float* g_elbo; float* terms;
   const kvae_cotangents* cot; const kvae_grads* grads; void* workspace;
   const DpView* dp;   // non-null: kvae_kf_bwd_dp -- the final kernel also does the cross-rank exchange
 };
@@ -32,7 +32,7 @@ template <int N, int P, int M, int K> struct ShapeOps {
                  float* C_list, int32_t* info, cudaStream_t s);
   static size_t elbo_ws(const kvae_dims& d);
   static int elbo(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const float* eps, float jitter,
-                  float* terms, void* ws, int32_t* info, cudaStream_t s);
+                  float jitter_q, int chol_diag, float* terms, void* ws, int32_t* info, cudaStream_t s);
   static size_t bwd_ws(const kvae_dims& d);
   static int bwd(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const BwdExtra& x, int32_t* info,
                  cudaStream_t s);

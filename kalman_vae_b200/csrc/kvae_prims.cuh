@@ -385,6 +385,26 @@ KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l
   return ok;
 }
 
+// chol_dist, or -- diag != 0 -- the last rung of the reference's _safe_cholesky ladder (kalman_filter.py:298-302):
+// L = diag(sqrt(clamp(diag(a), 1e-6))) (a: symmetrised, no jitter).  Never fails in that mode.
+template <int L, int R>
+KV_FN bool chol_dist_opt(const Group<L, R>& g, const float (&a)[R][L * R], float (&l)[R][L * R], float (&invd)[L * R],
+                         float (&dg_own)[R], int diag) {
+  if (!diag) return chol_dist<L, R>(g, a, l, invd, dg_own);
+  constexpr int N = L * R;
+  KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) l[r][j] = 0.f;
+  KV_UNROLL for (int j = 0; j < N; ++j) {
+    const int owner = j / R, jr = j % R;
+    float d = g.bcast(a[jr][j], owner);
+    d = sqrtf(d > 1e-6f ? d : 1e-6f);
+    invd[j] = 1.0f / d;
+    KV_UNROLL for (int r = 0; r < R; ++r) {
+      if (g.row0() + r == j) { l[r][j] = d; dg_own[r] = d; }
+    }
+  }
+  return true;
+}
+
 // x := x (Lc Lc^T)^-1 for each local row (Lc fully visible, invd = 1/diag(Lc) replicated).
 template <int R, int D, class V>
 KV_FN void solve_rows_llt(float (&x)[R][D], const V& Lc, const float (&invd)[D]) {

@@ -201,12 +201,13 @@ inline int seq_warps_per_cta(int B) {
   if (forced >= 1 && forced <= KV_SEQ_MAXWARPS) return forced;
   return ((B + 31) / 32 > 148 * 8) ? KV_SEQ_MAXWARPS : 2;
 }
-// Resident CTAs per SM are capped at TWO by requesting at least 100 KB of shared memory per CTA.  Measured on B200
-// (profiles/r02_seq_occupancy_sweep.log; B = 262 144, T = 20 and B = 32 768, T = 200): 8 warps per SM beat 12 in the forward
-// kernel (0.72 vs 0.83 ms: the smoother's read-back of the filter sweep's outputs finds more of them in L2) and 4 beat 6
-// in the adjoint (1.93 vs 2.31 ms: with three CTAs the unified L1/shared array has no L1 left for the adjoint's
-// register spills).  KVAE_SEQ_SMEM_FLOOR overrides the floor (development knob).
-inline size_t seq_smem_floor() { static const int v = seq_env_int("KVAE_SEQ_SMEM_FLOOR", 100 * 1024); return (size_t)v; }
+// Resident CTAs per SM are capped at TWO by requesting at least 78 KB of shared memory per CTA (3 x 79 KB > 227 KB) --
+// and not more, because the unified L1/shared array is carved per SM: what the CTAs do not take stays L1, which the
+// smoother's read-back loads and the adjoint's register spills live in.  Measured on B200 (B = 262 144, T = 20;
+// profiles/r02_seq_occupancy_sweep.log): forward 0.92 ms at three CTAs per SM, 0.78 ms at two with ~70 KB of L1, 1.05 ms
+// at two with 23 KB of L1 (100 KB requested per CTA); adjoint 2.31 / 1.93 / 2.6 ms.  KVAE_SEQ_SMEM_FLOOR overrides
+// the floor (development knob).
+inline size_t seq_smem_floor() { static const int v = seq_env_int("KVAE_SEQ_SMEM_FLOOR", 78 * 1024); return (size_t)v; }
 inline int seq_grid(int B) { const int per = 32 * seq_warps_per_cta(B); return (B + per - 1) / per; }
 
 struct SeqBar {   // mbarrier + the parity of its next completion
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
     }
   }
   if (warp_on) tma::wait_all0();   // the staging tiles must outlive their stores
-  if (!ok && active) *a.info = 1;
+  if (!ok && active) kv_info_or(a.info, KV_INFO_PIVOT);
 }
 
 

@@ -266,14 +266,15 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
     inv_norm = (float)(1.0 / (tot < 1.0 ? 1.0 : tot));
   }
   const float c = (*g_elbo) * (w.with_elbo ? inv_norm : terms[6]);
-  const float jit = w.jitter;
+  const CholOpt co = chol_opt(a, w.jitter);
   const uint64_t pol_ef = tma::policy_evict_first(), pol_el = tma::policy_evict_last();
 
   GA acc;
   acc.zero();
   acc.on = true;
   double el[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  bool ok = true;
+  bool ok = true, ok_s = true, ok_q = true;
+  int bad0 = 0;
   unsigned char* ib = wsm + PL::oIn;
   float* ax = reinterpret_cast<float*>(wsm + PL::oAx);
   unsigned char* sw = wsm + PL::oSw;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
       if (T > 1) issue_s3(0);
     }
     ElboConst<C> ec;
-    ok = elbo_const<C>(g, base, NT, jit, ec) && ok;
+    bad0 = elbo_const<C>(g, base, NT, co, ec);
     RegView<N, N> LQc_v{ec.LQ};
 
     ElboStep<C> es;
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
       TM::ld_mat(reinterpret_cast<const float*>(st1 + PL::s3_Ss), lane, Ss0);
       TV::ld(reinterpret_cast<const float*>(st1 + PL::s3_ms), lane, 0, ms0);
       TV::ld(reinterpret_cast<const float*>(st1 + PL::s3_ep), lane, 0, eps_cur);
-      ok = elbo_sample_rows<C>(g, NT, NT, Ss0, ms0, jit, eps_cur, es) && ok;
+      ok_s = elbo_sample_rows<C>(g, NT, NT, Ss0, ms0, co, eps_cur, es) && ok_s;
     }
     bar_in.wait();
     StepIn<C> in;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
       KV_UNROLL for (int r = 0; r < R; ++r) zbar[r] = xbar[r];
       float v_tr = 0.f, v_em = 0.f, v_in = 0.f, v_en = 0.f;
       if (has_next) {
-        ok = elbo_sample_rows<C>(g, NT, NT, Ss1, ms1, jit, eps1, es1) && ok;
+        ok_s = elbo_sample_rows<C>(g, NT, NT, Ss1, ms1, co, eps1, es1) && ok_s;
         float B1[R][M];
         mix_B<C>(base, in1.al, 0, B1);
         float x[N];
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
         if constexpr (C::QPM) {
           float Q1[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
           mix_Q<C>(base, in1.al, 0, Q1);
-          sym_jitter_rows<C>(g, Q1, NT, jit, Qs);
-          ok = chol_dist<1, R>(g, Qs, LQ, invdQ, dgQ) && ok;
+          sym_jitter_rows<C>(g, Q1, NT, co.diag_q ? 0.f : co.jq, Qs);
+          ok_q = chol_dist_opt<1, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
           RegView<N, N> LQ_v{LQ};
           solve_vec_l<N>(x, LQ_v, invdQ);
           if (w.with_elbo) {
@@ -408,7 +409,10 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
           float Qi[R][N];
           KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Qi[r][j] = (r == j) ? 1.f : 0.f;
           solve_rows_llt<R, N>(Qi, LQ_v, invdQ);
-          KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Qb[r][j] += 0.5f * c * (x[r] * x[j] - Qi[r][j]);
+          KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
+            const bool live = !co.diag_q || (r == j && dgQ[r] * dgQ[r] > 1e-6f);   // diagonal fallback: see kvae_bwd.cuh
+            Qb[r][j] += live ? 0.5f * c * (x[r] * x[j] - Qi[r][j]) : 0.f;
+          }
         } else {
           solve_vec_l<N>(x, LQc_v, ec.invdQ);
           if (w.with_elbo) {
@@ -494,7 +498,8 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
         float Phi[R][N];
         KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
           const float ve = v_own[r] * eps_cur[j];
-          Phi[r][j] = (j < r) ? ve : ((j == r) ? 0.5f * (ve + c) : 0.f);
+          const bool live_d = !co.diag_s || es.dg[r] * es.dg[r] > 1e-6f;
+          Phi[r][j] = (j < r) ? (co.diag_s ? 0.f : ve) : ((j == r && live_d) ? 0.5f * (ve + c) : 0.f);
         }
         solve_rows_l<R, N>(Phi, Ls_v, es.invd);
         float Zt[R][N];
@@ -844,7 +849,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
     }
     tma::wait_all0();
   }
-  if (!ok && active) *a.info = 1;
+  if (active) kv_info_or(a.info, bad0 | (ok ? 0 : KV_INFO_PIVOT) | (ok_s ? 0 : KV_INFO_CHOL_S) | (ok_q ? 0 : KV_INFO_CHOL_Q));
 
   // ---------------------------------------------------------------- per-CTA partial sums (fixed order -> deterministic)
   if (w.with_elbo) {

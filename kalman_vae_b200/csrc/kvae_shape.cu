@@ -30,6 +30,8 @@ Args make_args(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st,
   a.dA = in.A_dense; a.dB = in.B_dense; a.dC = in.C_dense; a.dQ = in.Q_dense;
   a.smooth_only = (d.flags & KVAE_FLAG_SMOOTH_ONLY) ? 1 : 0;
   a.mask_part = nullptr;
+  a.jitter_q = 1e-6f;
+  a.chol_diag = 0;
   a.info = info;
   return a;
 }
@@ -107,9 +109,11 @@ template <> size_t ShapeOps<N, P, M, K>::elbo_ws(const kvae_dims& d) {
 
 template <>
 int ShapeOps<N, P, M, K>::elbo(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, const float* eps,
-                               float jitter, float* terms, void* ws, int32_t* info, cudaStream_t s) {
+                               float jitter, float jitter_q, int chol_diag, float* terms, void* ws, int32_t* info, cudaStream_t s) {
   Args a = make_args(d, in, st, info);
   a.eps = eps;
+  a.jitter_q = jitter_q;
+  a.chol_diag = chol_diag;
   const BasePtrs bp = make_base(in);
   const bool sw = d.q_per_mode != 0;
 #define X(l)                                                                                     \
@@ -149,6 +153,8 @@ int ShapeOps<N, P, M, K>::bwd(const kvae_dims& d, const kvae_inputs& in, const k
                               int32_t* info, cudaStream_t s) {
   Args a = make_args(d, in, st, info);
   a.eps = x.eps;
+  a.jitter_q = x.jitter_q;
+  a.chol_diag = x.chol_diag;
   const BasePtrs bp = make_base(in);
   BwdArgs w{};
   if (x.cot) {

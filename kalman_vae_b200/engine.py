@@ -28,7 +28,7 @@ from .functional import Problem, States, info_word
 
 class KalmanStep:
     def __init__(self, pb: Problem, eps: torch.Tensor, jitter: float = 1e-6, use_graphs: bool = True, group=None,
-                 lists: bool = True, need_dU: bool = False):
+                 lists: bool = True, need_dU: bool = False, collective: str | None = None):
         self.pb, self.eps, self.jitter, self.group = pb, eps, jitter, group
         B, T, n, p, m, K = pb.shape
         dev = pb.Y.device
@@ -69,7 +69,7 @@ class KalmanStep:
         self.collective = "none"
         if self.world > 1:
             self.collective = "nccl"
-            mode = os.environ.get("KVAE_DP_COLLECTIVE", "peer")   # peer: fused into the adjoint's final kernel (kvae_kf_bwd_dp);
+            mode = collective or os.environ.get("KVAE_DP_COLLECTIVE", "peer")   # peer: fused into the adjoint's final kernel (kvae_kf_bwd_dp);
             self.peer_two_launch = (mode == "peer2")                # peer2: kvae_kf_bwd + kvae_dp_finalize; nccl: torch.distributed
             if mode in ("peer", "peer2"):
                 try:
@@ -139,6 +139,24 @@ class KalmanStep:
                 self._post()
         return self.terms
 
+    def check(self):
+        """Host-side look at the device status word (ONE synchronising read: call it when the results are consumed, not
+        per launch).  Raises if a factorisation met a non-positive pivot (1: the reference would raise or retry with a
+        larger jitter, kalman_filter.py:282-302) or if the data-parallel exchange gave up waiting for a peer (2: the
+        gradients of that step were NOT written)."""
+        code = int(self.info.item())
+        if code & capi.INFO_PEER:
+            raise RuntimeError("kvae: the data-parallel exchange timed out waiting for a peer; gradients of this step are invalid")
+        if code:
+            raise torch.linalg.LinAlgError(f"kvae: a Cholesky / LU pivot was not positive in this step (status word {code}: "
+                                           "1 filter/smoother, 4 Sigma_smooth, 8 Q)")
+
+    def close(self):
+        """Releases the peer-memory exchange (CUDA IPC mappings); the object must not be stepped afterwards."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+
     def forward_only(self):
         """smooth only (the imputation path): one launch, no collective."""
         capi.filter_smooth_fwd(self.pb.dims, self._inputs, self._states, self.A_list, self.B_list, self.C_list,
@@ -168,15 +186,32 @@ class HostPipeline:
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.compute_stream = torch.cuda.Stream(device=dev)
-        self.inputs, self.steps, self.out_host = [], [], []
+        self.inputs, self.steps, self.out_host, self.info_host = [], [], [], []
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
         self.ev_free = [torch.cuda.Event() for _ in range(slots)]
         self.ev_out = [torch.cuda.Event() for _ in range(slots)]
         self._used = [False] * slots
         with torch.cuda.stream(self.compute_stream):
+            # the per-step inputs of a slot are views into ONE device slab (256-byte aligned pieces), mirrored by a pinned
+            # host slab (host_slab()): a caller that fills the host views moves a whole step with one cudaMemcpyAsync
+            self._layout, off = {}, 0
+            for name, shp in (("Y", (B, T, p)), ("U", (B, T, m) if has_U else None), ("mask", (B, T) if has_mask else None),
+                              ("alpha", (B, T, K)), ("eps", (B, T, n))):
+                if shp is None:
+                    continue
+                cnt = 1
+                for v in shp:
+                    cnt *= v
+                self._layout[name] = (off, cnt, shp)
+                off += (cnt + 63) & ~63
+            self._slab_floats = off
+            self.slabs = []
             for _ in range(slots):
-                d = dict(Y=e(B, T, p), U=e(B, T, m) if has_U else None, mask=e(B, T) if has_mask else None,
-                         alpha=e(B, T, K), eps=e(B, T, n))
+                slab = e(off)
+                self.slabs.append(slab)
+                view = lambda nm: slab[self._layout[nm][0]:self._layout[nm][0] + self._layout[nm][1]].view(*self._layout[nm][2])
+                d = dict(Y=view("Y"), U=view("U") if has_U else None, mask=view("mask") if has_mask else None,
+                         alpha=view("alpha"), eps=view("eps"))
                 for t in d.values():   # defined contents for the graph-capture warm-up run
                     if t is not None:
                         t.zero_()
@@ -188,9 +223,10 @@ class HostPipeline:
                 self.inputs.append(d)
                 self.steps.append(KalmanStep(pb, d["eps"], jitter=jitter, use_graphs=True, group=group, need_dU=False))
                 self.out_host.append(torch.empty(self.steps[-1].flat.numel(), dtype=torch.float32).pin_memory())
+                self.info_host.append(torch.zeros(1, dtype=torch.int32).pin_memory())
         self.compute_stream.synchronize()
         self.h2d_bytes_per_step = sum(t.numel() * 4 for t in self.inputs[0].values() if t is not None)
-        self.d2h_bytes_per_step = self.out_host[0].numel() * 4
+        self.d2h_bytes_per_step = self.out_host[0].numel() * 4 + 4
         self.i = 0
 
     def step(self, Y, U, mask, alpha, eps):
@@ -208,11 +244,33 @@ class HostPipeline:
                 if d[name] is not None and src is not None:
                     d[name].copy_(src, non_blocking=True)
             self.ev_in[k].record(self.copy_stream)
+        return self._launch(k)
+
+    def host_slab(self):
+        """A pinned host buffer with the slot layout and its named views {Y, U, mask, alpha, eps}: fill the views
+        (e.g. as the collate buffer of a data loader), then pass the slab to step_packed()."""
+        slab = torch.empty(self._slab_floats, dtype=torch.float32).pin_memory()
+        views = {nm: slab[o:o + c].view(*shp) for nm, (o, c, shp) in self._layout.items()}
+        return slab, views
+
+    def step_packed(self, slab):
+        """step() for a host_slab(): the five inputs cross PCIe as ONE copy."""
+        k = self.i % self.slots
+        self.i += 1
+        with torch.cuda.stream(self.copy_stream):
+            if self._used[k]:
+                self.copy_stream.wait_event(self.ev_free[k])
+            self.slabs[k].copy_(slab, non_blocking=True)
+            self.ev_in[k].record(self.copy_stream)
+        return self._launch(k)
+
+    def _launch(self, k):
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.ev_in[k])
             self.steps[k].step()
             self.ev_free[k].record(self.compute_stream)
             self.out_host[k].copy_(self.steps[k].flat, non_blocking=True)
+            self.info_host[k].copy_(self.steps[k].info, non_blocking=True)   # status word travels with the results
             self.ev_out[k].record(self.compute_stream)
         self._used[k] = True
         return k
@@ -221,8 +279,18 @@ class HostPipeline:
         """Blocks until step `k`'s results are in host memory.  Returns (elbo, flat_host) where flat_host is the pinned
         buffer [dA | dB | dC | dQ | pad | terms(8)] of that slot (valid until the slot is used again)."""
         self.ev_out[k].synchronize()
+        code = int(self.info_host[k][0])
+        if code:   # bit 2: a peer never arrived and the gradients of this step were not written; else a non-positive pivot
+            self.steps[k].info.zero_()
+            raise (RuntimeError if code & capi.INFO_PEER else torch.linalg.LinAlgError)(
+                "kvae: " + ("the data-parallel exchange timed out waiting for a peer; this step's gradients are invalid"
+                            if code & capi.INFO_PEER else f"a Cholesky / LU pivot was not positive (status word {code})"))
         out = self.out_host[k]
         return float(out[out.numel() - 3]), out   # terms[5]
+
+    def close(self):
+        for s in self.steps:
+            s.close()
 
     def device_grads(self, k):
         """dY, dalpha (+ parameter-gradient views) of slot k on the device, ordered on the compute stream."""

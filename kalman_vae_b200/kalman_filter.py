@@ -40,7 +40,7 @@ def _tag(t, prov):
 
 
 class KalmanFilter(nn.Module):
-    def __init__(self, std_dyn, std_obs, mu0, Sigma0, dyn_params, lanes=0, check_info=True):
+    def __init__(self, std_dyn, std_obs, mu0, Sigma0, dyn_params, lanes=0, check_info="lazy"):
         super().__init__()
         self.dyn_params = dyn_params
         n = dyn_params.A.size(1)
@@ -54,10 +54,17 @@ class KalmanFilter(nn.Module):
         self.register_buffer("mu0", mu0.clone())
         self.register_buffer("Sigma0", Sigma0.clone())
         self.lanes = lanes              # 0: library picks lanes per sequence
-        self.check_info = check_info    # read the device 'non-positive pivot' flag after elbo()
-        self.strict = True              # verify that elbo() sees the same y/mask values as smooth()
-        self._mask_cache = None
+        # what happens with the device status word ('a factorisation met a non-positive pivot') after elbo():
+        #   "lazy" (default): no host synchronisation; the word is copied to pinned host memory and looked at when the
+        #                     NEXT call of this object starts -- a failure raises one call late
+        #   True            : read it right away (one host sync per elbo()) and run the reference's _safe_cholesky
+        #                     ladder (kalman_filter.py:282-302: 10x jitter per retry, separately for Sigma_smooth and Q,
+        #                     clamped-diagonal fallback after five tries)
+        #   False           : never look
+        self.check_info = check_info
+        self.strict = False             # True: verify (host syncs) that elbo() sees the same y / u / mask VALUES as smooth()
         self._prep_cache = {}
+        self._deferred = []             # [(event, pinned int32 word, kind)] device-side checks read one call late
 
     # ------------------------------------------------------------------ helpers
     def _mask(self, mask, B, T, ref):
@@ -68,16 +75,38 @@ class KalmanFilter(nn.Module):
             m = m.view(B, T)                                         # kalman_filter.py:131-133
         return m
 
-    def _mask_is_ones(self, mask):
-        """True when every entry is 1 (one host sync, cached on the tensor's identity/version)."""
-        if mask is None:
-            return True
-        key = (mask.data_ptr(), mask._version, tuple(mask.shape))
-        if self._mask_cache is not None and self._mask_cache[0] == key:
-            return self._mask_cache[1]
-        val = bool((mask == 1).all().item())
-        self._mask_cache = (key, val)
-        return val
+    # ------------------------------------------------------------------ deferred device-side checks
+    def _defer(self, flag, kind):
+        """Queues a device int32 `flag` (non-zero = failure) for a look at the start of the next public call."""
+        host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        host.copy_(flag.reshape(1).to(torch.int32), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flag.device))
+        self._deferred.append((ev, host, kind))
+        if len(self._deferred) > 8:      # never let the queue grow: wait for the oldest entry
+            self._poll_deferred(block_oldest=True)
+
+    def _poll_deferred(self, block_oldest=False):
+        keep = []
+        for i, (ev, host, kind) in enumerate(self._deferred):
+            if block_oldest and i == 0:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((ev, host, kind))
+                continue
+            code = int(host[0])
+            if code:
+                self._deferred = []
+                if kind == "mask":
+                    raise NotImplementedError(
+                        "an earlier filter()/smooth() call with lstm dynamics and gradients enabled had missing observations "
+                        "(mask != 1): that combination is forward-only here (the reference feeds C mu_pred to the LSTM at "
+                        "missing steps, kalman_filter.py:183-185); wrap such calls in torch.no_grad()")
+                raise torch.linalg.LinAlgError(
+                    "kvae: a factorisation in an earlier elbo() call met a non-positive pivot (status word "
+                    f"{code}); construct KalmanFilter(..., check_info=True) to get the reference's jitter ladder "
+                    "(kalman_filter.py:282-302) instead of this late report")
+        self._deferred = keep
 
     def _lstm_alpha_batched(self, Y):
         """alpha [B,T,K] of the LSTM dynamics network for a fully observed sequence, one cuDNN call
@@ -132,12 +161,25 @@ class KalmanFilter(nn.Module):
         B, T, _ = Y.shape
         mask_t = self._mask(mask, B, T, Y)
         dyn = self.dyn_params
-        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and not self._mask_is_ones(mask_t):
-            if torch.is_grad_enabled() and (Y.requires_grad or any(p.requires_grad for p in dyn.parameters())):
-                raise NotImplementedError(
-                    "lstm dynamics with missing observations is forward-only here (imputation, as in "
-                    "KVAE.impute); wrap the call in torch.no_grad()")
-            return self._run_stepwise_lstm(Y, U, mask_t, smooth)
+        self._poll_deferred()
+        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and mask_t is not None:
+            # lstm dynamics + a mask: alpha_{t+1} depends on the running prediction wherever mask_t = 0
+            # (kalman_filter.py:159,183-185).  No host look at the mask's values:
+            #  * no gradient wanted (imputation, evaluation): the LSTM runs inside the filter kernel -- exact for ANY mask;
+            #  * gradient wanted (training): the batched-alpha path, which equals the reference iff mask == 1 everywhere
+            #    (what the reference's trainer passes, train.py:41); a device-side test of that is read one call late
+            #    (immediately with strict=True).
+            wants_grad = torch.is_grad_enabled() and (Y.requires_grad or any(p.requires_grad for p in dyn.parameters()))
+            if not wants_grad:
+                return self._run_stepwise_lstm(Y, U, mask_t, smooth)
+            bad = (mask_t != 1).any()
+            if self.strict:
+                if bool(bad.item()):
+                    raise NotImplementedError(
+                        "lstm dynamics with missing observations is forward-only here (imputation, as in "
+                        "KVAE.impute); wrap the call in torch.no_grad()")
+            else:
+                self._defer(bad, "mask")
         alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
         pb = self._problem(Y, U, mask_t, alpha, A, Bm, C, Q, qpm, csh)
         diff = (Y, U, alpha, A, Bm, C, Q if qpm else None)
@@ -169,8 +211,6 @@ class KalmanFilter(nn.Module):
         """lstm dynamics with missing observations: alpha_t depends on the running prediction
         (kalman_filter.py:159,183-185), so the filter advances one step per launch with the LSTM cell
         in between; the smoother then runs as one launch over the stored states."""
-        if torch.is_grad_enabled() and (Y.requires_grad or any(p.requires_grad for p in self.dyn_params.parameters())):
-            pass  # under torch.no_grad() this is never reached with grad enabled
         dyn = self.dyn_params
         B, T, p = Y.shape
         dev = Y.device
@@ -203,20 +243,7 @@ class KalmanFilter(nn.Module):
         mf, Sf, mp, Sp, A_list, B_list, C_list = (bt(x) for x in (mf, Sf, mp, Sp, Al, Bl, Cl))
         if not smooth:
             return mf, Sf, mp, Sp, A_list, B_list, C_list
-        # smoother sweep over the stored filter states (one launch, no refiltering)
-        pb = Problem(prep(Y), prep(U), prep(mask_t), prep(alpha), prep(dyn.A, dev), prep(dyn.B, dev), prep(dyn.C, dev),
-                     prep(self.Q, dev), prep(self.R, dev), prep(self.mu0, dev), prep(self.Sigma0, dev), False, False,
-                     lanes=self.lanes, flags=F.capi.FLAG_SMOOTH_ONLY)
-        st = States(mf, Sf, mp, Sp, torch.empty_like(mf), torch.empty_like(Sf))
-        F.capi.filter_smooth_fwd(pb.dims, pb.inputs(), st.c_struct(), None, None, None, F.info_word(dev), dev)
-        pb.flags = 0
-        pb.dims.flags = 0
-        prov = _Provenance(pb, st, (Y, U, alpha, dyn.A, dyn.B, dyn.C, None), True)
-        prov.mus_smooth_ref = weakref.ref(st.mus_smooth)
-        prov.Sigmas_smooth_ref = weakref.ref(st.Sigmas_smooth)
-        for t_ in (A_list, B_list, C_list):
-            _tag(t_, prov)
-        return (st.mus_smooth, st.Sigmas_smooth, mf, Sf, mp, Sp, A_list, B_list, C_list)
+        return self._smooth_from_filtered(Y, U, mask_t, alpha, mf, Sf, mp, Sp, A_list, B_list, C_list)
 
     def _run_fused_lstm(self, Y, U, mask_t, smooth):
         """The same recursion as the stepwise loop below in ONE launch: the LSTM cell, the head and the softmax run
@@ -306,7 +333,8 @@ class KalmanFilter(nn.Module):
         B, T, _ = Y.shape
         mask_t = self._mask(mask, B, T, Y)
         dyn = self.dyn_params
-        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and not self._mask_is_ones(mask_t):
+        self._poll_deferred()
+        if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and mask_t is not None:
             outs = self._run_stepwise_lstm(Y, U, mask_t, True)          # fused LSTM launch (or the per-step fallback)
             ms, mf, alpha, csh = outs[0], outs[2], dyn.state_seq, False
         else:
@@ -364,18 +392,40 @@ class KalmanFilter(nn.Module):
             pb2 = Problem(prep(y_t), prep(u3), prep(mask_t), pb.alpha, pb.A, pb.Bm, pb.C, pb.Q, pb.R, pb.mu0, pb.Sigma0,
                           pb.q_per_mode, pb.c_shared, lanes=self.lanes)
             run = lambda jit: F.ElboFunction.apply(pb2, eps, jit, extra, mu_t_T, Sigma_t_T, y_t, u3, alpha, A, Bm, C, Q)
-        jitter = 1e-6
-        for attempt in range(5):                                                  # _safe_cholesky ladder (:291-296)
+        info = F.info_word(dev)
+        if self.check_info is not True:
+            # one launch with the reference's first rung (jitter 1e-6 on both factorisations); no host synchronisation:
+            # the status word is looked at when the next call of this object starts ("lazy") or never (False)
             if self.check_info:
-                F.info_word(dev).zero_()
-            val = run(jitter)
-            if not self.check_info or int(F.info_word(dev).item()) == 0:
+                info.zero_()
+            val = run(1e-6)
+            if self.check_info:
+                self._defer(info.clone(), "chol")
+            return val
+        # the reference's _safe_cholesky ladder (kalman_filter.py:282-302), one ladder per factorised family as there:
+        # any failing matrix bumps the jitter of its family 10x for the WHOLE batch (:295-296); after five failed
+        # attempts the family falls back to L = diag(sqrt(clamp(diag, 1e-6))) (:298-302)
+        js = jq = 1e-6
+        ds = dq = False
+        fails_s = fails_q = 0
+        while True:
+            info.zero_()
+            val = run((js, jq, ds, dq))
+            code = int(info.item())
+            if code & F.capi.INFO_PIVOT:
+                raise torch.linalg.LinAlgError("kvae elbo: a pivot of the filter / smoother / R / Sigma0 factorisations was not positive")
+            retry = False
+            if (code & F.capi.INFO_CHOL_S) and not ds:
+                fails_s += 1
+                ds, js = (True, js) if fails_s >= 5 else (False, js * 10.0)
+                retry = True
+            if (code & F.capi.INFO_CHOL_Q) and not dq:
+                fails_q += 1
+                dq, jq = (True, jq) if fails_q >= 5 else (False, jq * 10.0)
+                retry = True
+            if not retry:
                 break
-            jitter *= 10.0      # a factorisation met a non-positive pivot: retry everything with 10x jitter
-        else:
-            raise torch.linalg.LinAlgError(
-                "kvae elbo: Cholesky failed for every jitter up to 1e-2 (the reference would fall back to the "
-                "clamped diagonal here, kalman_filter.py:298-302)")
+        self.last_chol = dict(jitter_smooth=js, jitter_q=jq, diag_smooth=ds, diag_q=dq)
         return val
 
     def _draw_eps(self, B, T, n, like):

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE — live import of the UNMODIFIED reference (rodrigo-paganini/kalman-vae).
 
-Only usable where the reference checkout exists (this build container: /root/reference).
-It never travels to the GPU box; everything the GPU box needs from the reference is exported
-as golden vectors by `oracle/make_golden.py` into `tests/golden/`.
+Usable where the reference sources exist: the checkout of the build container (/root/reference) or the
+pip-installed copy under baseline/_ref (oracle/install_reference.sh; git-ignored, it travels to the GPU box).
+Everything the GPU parity tests need from the reference is ALSO exported as golden vectors by
+`oracle/make_golden.py` into `tests/golden/`, so they do not depend on either.
 
 Two import shims are required:
   * kvae/kalman/kalman_filter.py:5 imports matplotlib (unused, not installed)
@@ -19,7 +20,10 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOTS = ("/root/reference",)
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the read-only checkout of the build container, then the pip-installed copy that travels to the GPU box
+# (oracle/install_reference.sh -> baseline/_ref)
+REFERENCE_ROOTS = ("/root/reference", os.path.join(_REPO, "baseline", "_ref"))
 
 
 def reference_root():
@@ -42,7 +46,7 @@ def load():
         return types.SimpleNamespace(**_loaded)
     root = reference_root()
     if root is None:
-        raise RuntimeError("reference checkout not found (expected /root/reference)")
+        raise RuntimeError("reference sources not found (expected /root/reference or baseline/_ref)")
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
         plt = types.ModuleType("matplotlib.pyplot")

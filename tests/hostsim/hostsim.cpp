@@ -71,6 +71,7 @@ extern "C" int hostsim_elbo(int N, int P, int M, int K, int switching, int force
   Args a{};
   a.B = B; a.T = T; a.Y = Y; a.U = U; a.mask = mask; a.alpha = alpha; a.eps = eps;
   a.mu_s = mu_s; a.Sig_s = Sig_s; a.info = info;
+  a.jitter_q = jitter; a.chol_diag = 0;
   HostParams hp{A, Bm, C, Q, R, mu0, S0};
 #define X(n, p, m, k)                                                                                   \
   if (N == n && P == p && M == m && K == k) {                                                           \
@@ -139,6 +140,7 @@ extern "C" int hostsim_bwd(int N, int P, int M, int K, int switching, int force_
   Args a{};
   a.B = B; a.T = T; a.Y = Y; a.U = U; a.mask = mask; a.alpha = alpha; a.eps = eps;
   a.mu_f = mu_f; a.Sig_f = Sig_f; a.mu_p = mu_p; a.Sig_p = Sig_p; a.mu_s = mu_s; a.Sig_s = Sig_s; a.info = info;
+  a.jitter_q = jitter; a.chol_diag = 0;
   BwdArgs w{};
   w.c_mu_s = cot9[0]; w.c_Sig_s = cot9[1]; w.c_mu_f = cot9[2]; w.c_Sig_f = cot9[3]; w.c_mu_p = cot9[4]; w.c_Sig_p = cot9[5];
   w.c_A = cot9[6]; w.c_B = cot9[7]; w.c_C = cot9[8];

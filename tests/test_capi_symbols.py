@@ -28,11 +28,12 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_support_table(lib):
     L = capi.lib()
-    assert L.kvae_abi_version() == 5
+    assert L.kvae_abi_version() == 6
     ok = capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 0)
     assert capi.supported(ok)
     assert capi.pick_lanes(ok) == 4                      # small batch -> widest lane group
-    assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 4   # one row per lane wins at every size
+    assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 1   # >= 32768 sequences, T % 4 == 0: thread per sequence
+    assert capi.pick_lanes(capi.make_dims(65536, 1001, 4, 2, 4, 3, False, False, 0)) == 4   # T % 4 != 0: lane groups
     assert capi.supported(capi.make_dims(8, 20, 16, 8, 16, 8, True, True, 16))
     assert not capi.supported(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0))     # shape not instantiated
     assert not capi.supported(capi.make_dims(8, 20, 4, 2, 4, 3, True, False, 0))      # mixed variant

@@ -294,3 +294,129 @@ def test_lstm_in_the_loop_kernel_matches_stepwise_path(shape, hidden):
     assert rel(f[4], s[4]) < 2e-5 and rel(f[5], s[5]) < 2e-5                               # carried (h, c)
     miss = mask == 0                                                                        # mask handling stays bit-exact
     assert torch.equal(f[0][2][miss], f[0][4][miss])
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# _safe_cholesky ladder THROUGH THE KERNELS (kalman_filter.py:282-302): the kernels report which family failed in the
+# status word, KalmanFilter(check_info=True).elbo re-launches with the reference's next rung (10x jitter for the whole
+# batch, separately for Sigma_smooth and Q; clamped-diagonal fallback after five failures).  Expected values: the oracle
+# (same ladder, pinned to the live reference by tests/test_oracle.py::test_safe_cholesky_ladder_matches_reference).
+# --------------------------------------------------------------------------------------------------------------------
+def _ladder_case(min_eig):
+    """kalman_lstm golden with ONE smoothed covariance pushed to smallest eigenvalue `min_eig`."""
+    from oracle import kalman_oracle as ko
+    case = load_golden("kalman_lstm")[0]
+    g = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in case.items()}
+    outs, Q_seq = ko.smooth(g["Y"], g["U"], g["mask"], g["alpha"], g["A"], g["B"], g["C"], g["Q"], g["R"], g["mu0"], g["Sigma0"],
+                            bool(g["c_shared"]), bool(g["q_per_mode"]))
+    ms, Ss = outs[0].squeeze(-1).clone(), outs[1].clone()
+    S = 0.5 * (Ss[1, 3] + Ss[1, 3].T)
+    w, V = torch.linalg.eigh(S.double())
+    v = V[:, 0]
+    Ss[1, 3] = (S.double() - (w[0] - min_eig) * torch.outer(v, v)).float()
+    return g, outs, Q_seq, ms, Ss
+
+
+@pytest.mark.parametrize("min_eig,rung", [(-5e-6, "1e-5"), (-1.0, "diag")])
+def test_safe_cholesky_ladder_through_the_kernels(min_eig, rung):
+    from oracle import kalman_oracle as ko
+    g, outs, Q_seq, ms, Ss = _ladder_case(min_eig)
+    ref = {}
+    for dt in (torch.float32, torch.float64):
+        c = lambda x: x.to(dt)
+        m_, S_ = c(ms).requires_grad_(True), c(Ss).requires_grad_(True)
+        val = ko.elbo(m_, S_, c(g["Y"]), c(g["U"]), c(outs[6]), c(outs[7]), c(outs[8]), c(Q_seq), c(g["R"]), c(g["mu0"]),
+                      c(g["Sigma0"]), c(g["mask"]), c(g["eps"]))
+        gm, gS = torch.autograd.grad(val, [m_, S_])
+        ref[dt] = (val.detach(), gm, gS)
+    kf, dyn = make_kf(g)
+    kf.check_info = True
+    d = lambda x: x.to(DEV)
+    res = kf.smooth(d(g["Y"]), d(g["U"]), d(g["mask"]))
+    mu_in, S_in = d(ms).requires_grad_(True), d(Ss).requires_grad_(True)
+    kf._draw_eps = lambda B, T, n, like: d(g["eps"])
+    val = kf.elbo(mu_in, S_in, d(g["Y"]), d(g["U"]), res[6], res[7], res[8], mask=d(g["mask"]))
+    gm, gS = torch.autograd.grad(val, [mu_in, S_in])
+    if rung == "diag":
+        assert kf.last_chol["diag_smooth"] is True and kf.last_chol["diag_q"] is False
+    else:
+        assert abs(kf.last_chol["jitter_smooth"] - 1e-5) < 1e-12 and kf.last_chol["jitter_q"] == 1e-6, kf.last_chol
+        assert kf.last_chol["diag_smooth"] is False
+    check_close(f"ladder[{rung}].elbo", val, ref[torch.float32][0], ref[torch.float64][0])
+    check_close(f"ladder[{rung}].dmu", gm, ref[torch.float32][1], ref[torch.float64][1], rtol=5e-5)
+    check_close(f"ladder[{rung}].dSigma", gS, ref[torch.float32][2], ref[torch.float64][2], rtol=5e-5)
+
+
+def test_safe_cholesky_q_ladder_fused_path():
+    """Switching dynamics with a learnable Q_k that is not positive definite (smallest eigenvalue of the mixture -5e-6):
+    the Q ladder climbs to 1e-5 while the Sigma_smooth ladder stays at 1e-6; fused value + adjoint launch."""
+    from oracle import kalman_oracle as ko
+    case = load_golden("kalman_switch")[0]
+    g = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in case.items()}
+    n = g["A"].shape[-1]
+    g["Q"] = g["Q"] - (torch.linalg.eigvalsh(0.5 * (g["Q"] + g["Q"].mT).double()).min().float() + 5e-6) * torch.eye(n)
+    r32 = ko.run_case(g, torch.float32, want_grads=True)
+    r64 = ko.run_case(g, torch.float64, want_grads=True)
+    kf, dyn = make_kf(g)
+    kf.check_info = True
+    d = lambda x: x.to(DEV)
+    Y = d(g["Y"]).requires_grad_(True)
+    res = kf.smooth(Y, d(g["U"]), d(g["mask"]))
+    kf._draw_eps = lambda B, T, n_, like: d(g["eps"])
+    val = kf.elbo(res[0], res[1], Y, d(g["U"]), res[6], res[7], res[8], mask=d(g["mask"]))
+    gY, gQ, gA = torch.autograd.grad(val, [Y, dyn.Q, dyn.A])
+    assert kf.last_chol["jitter_q"] > 5e-6 and kf.last_chol["jitter_smooth"] == 1e-6, kf.last_chol
+    check_close("qladder.elbo", val, r32["elbo"], r64["elbo"])
+    check_close("qladder.dQ", gQ, r32["dQ"], r64["dQ"], rtol=5e-5)
+    check_close("qladder.dA", gA, r32["dA"], r64["dA"], rtol=5e-5)
+    check_close("qladder.dY", gY, r32["dY"], r64["dY"], rtol=5e-5)
+
+
+def test_lazy_status_word_reports_one_call_late():
+    """check_info='lazy' (the default): no host synchronisation in elbo(); a failed factorisation raises when the next
+    call of the object starts."""
+    g, outs, Q_seq, ms, Ss = _ladder_case(-1.0)
+    kf, dyn = make_kf(g)
+    assert kf.check_info == "lazy"
+    d = lambda x: x.to(DEV)
+    res = kf.smooth(d(g["Y"]), d(g["U"]), d(g["mask"]))
+    kf._draw_eps = lambda B, T, n, like: d(g["eps"])
+    kf.elbo(d(ms), d(Ss), d(g["Y"]), d(g["U"]), res[6], res[7], res[8], mask=d(g["mask"]))   # does not raise
+    torch.cuda.synchronize()
+    with pytest.raises(torch.linalg.LinAlgError):
+        kf.smooth(d(g["Y"]), d(g["U"]), d(g["mask"]))
+
+
+def test_lstm_mask_after_ones_mask_takes_the_in_kernel_lstm_path():
+    """an all-ones mask followed by a FRESH mask with zeros of the same shape (possibly at the same
+    address) must not be treated as all-ones: under no_grad the LSTM runs in the filter kernel for any mask."""
+    z = np.load(os.path.join(GOLDEN, "kvae_lstm.npz"))
+    K, n, p, m = int(z["K"]) if "K" in z.files else 3, 4, 2, 4
+    torch.manual_seed(0)
+    A = torch.eye(n).repeat(3, 1, 1) + 0.05 * torch.randn(3, n, n)
+    dyn = DynamicsParameter(A, 0.05 * torch.randn(3, n, m), 0.3 * torch.randn(3, p, n)).to(DEV)
+    with torch.no_grad():
+        dyn.head_w.bias.zero_()
+    kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, torch.zeros(n), 20 * torch.eye(n), dyn).to(DEV)
+    B, T = 64, 20
+    Y = torch.randn(B, T, p, device=DEV) * 0.5
+    U = torch.zeros(B, T, m, device=DEV)
+    with torch.no_grad():
+        dyn.reset_state()
+        ones = torch.ones(B, T, device=DEV)
+        o1 = kf.smooth(Y, U, ones)
+        a1 = dyn.state_seq.clone()
+        del ones
+        dyn.reset_state()
+        holes = torch.ones(B, T, device=DEV)
+        holes[:, 4:16] = 0.0
+        o2 = kf.smooth(Y, U, holes)
+        a2 = dyn.state_seq.clone()
+        # reference semantics for the masked call: the per-step path (LSTM cell + one filter launch per step)
+        dyn.reset_state()
+        kf.lanes = 2          # lanes != n disables the fused LSTM launch -> per-step fallback
+        o3 = kf.smooth(Y, U, holes)
+        a3 = dyn.state_seq.clone()
+    assert not torch.allclose(a1[:, 6:], a2[:, 6:], atol=1e-4)          # the masked call did NOT reuse the batched alphas
+    assert float((a2 - a3).abs().max()) < 5e-5                           # ... it fed C mu_pred to the LSTM at missing steps
+    assert float((o2[0] - o3[0]).norm() / o3[0].norm()) < 5e-5

@@ -78,3 +78,22 @@ def test_steady_state_riccati_known_answer():
     P = out["Sigmas_pred"][0, -1, 0, 0].item()
     a, c, q, r = (float(torch.tensor(v, dtype=torch.float32)) for v in (a, c, q, r))   # inputs are stored in fp32
     assert abs(P - (a * a * P * r / (c * c * P + r) + q)) < 1e-12
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference sources not present")
+@pytest.mark.parametrize("min_eig", [1e-3, -5e-6, -2e-4, -1.0])
+def test_safe_cholesky_ladder_matches_reference(min_eig):
+    """The oracle's ladder (which the GPU ladder tests are checked against) against the live reference's
+    KalmanFilter._safe_cholesky (kalman_filter.py:282-302): first rung, a higher rung, the clamped-diagonal fallback."""
+    ns = ref_shim.load()
+    torch.manual_seed(3)
+    X = torch.randn(5, 7, 4, 4, dtype=torch.float64)
+    S = X @ X.mT + 0.5 * torch.eye(4, dtype=torch.float64)
+    w, V = torch.linalg.eigh(S[2, 3])
+    S[2, 3] = S[2, 3] - (w[0] - min_eig) * torch.outer(V[:, 0], V[:, 0])
+    S = S + 1e-3 * torch.randn(5, 7, 4, 4, dtype=torch.float64)          # not exactly symmetric, as Sigma_pred is
+    kf = ns.KalmanFilter.__new__(ns.KalmanFilter)                         # the method uses no instance state
+    for dt in (torch.float64, torch.float32):
+        L_ref = ns.KalmanFilter._safe_cholesky(kf, S.to(dt))
+        L = ko.safe_cholesky(S.to(dt))
+        assert torch.equal(L, L_ref), (min_eig, dt)
