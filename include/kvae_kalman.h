@@ -104,6 +104,12 @@ typedef struct kvae_states {
    * finds it non-NULL applies 1/max(sum mask,1) inside its sweep instead of re-scaling dY/dalpha/dU afterwards.  It must
    * come from a forward call on the SAME mask and dims (incl. lanes).  NULL = not used. */
   float* mask_partials;
+  /* optional outputs of the FORWARD entry ([B,T,p] each; NULL = not wanted): the observation-space projections
+   * KVAE.impute forms after smoothing, a_filtered = C_t mu_{t|t} (kvae/model/model.py:287-288) and
+   * a_imputed = C_t mu_{t|T} (:280-281), emitted by the filter / smoother sweeps themselves (C_t is in registers there).
+   * a_smooth needs mus_smooth / Sigmas_smooth (the smoother sweep); both are ignored by the ELBO / backward entries. */
+  float* a_filt;
+  float* a_smooth;
 } kvae_states;
 
 int kvae_abi_version(void);

@@ -26,7 +26,7 @@ class KvaeInputs(Structure):
 
 class KvaeStates(Structure):
     _fields_ = [(k, c_void_p) for k in ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred",
-                                        "mus_smooth", "Sigmas_smooth", "mask_partials")]
+                                        "mus_smooth", "Sigmas_smooth", "mask_partials", "a_filt", "a_smooth")]
 
 
 class KvaeCotangents(Structure):
@@ -125,17 +125,20 @@ EXPORTED_SYMBOLS = [
 def _ptr(t, name, device=None):
     if t is None:
         return None
-    if not t.is_cuda:
-        raise KvaeError(f"{name}: expected a CUDA tensor (the Kalman hot path has no CPU implementation)")
-    if t.dtype != torch.float32 and t.dtype != torch.int32:
-        raise KvaeError(f"{name}: expected float32, got {t.dtype}")
-    if not t.is_contiguous():
-        raise KvaeError(f"{name}: expected a contiguous tensor")
-    if t.data_ptr() % 16 != 0:
-        raise KvaeError(f"{name}: base pointer must be 16-byte aligned")
-    if device is not None and t.device != device:
+    p = t.data_ptr()
+    # one combined test on the hot path; the specific message is worked out only when it fails
+    if not (t.is_cuda and (t.dtype is torch.float32 or t.dtype is torch.int32) and t.is_contiguous() and p % 16 == 0
+            and (device is None or t.device == device)):
+        if not t.is_cuda:
+            raise KvaeError(f"{name}: expected a CUDA tensor (the Kalman hot path has no CPU implementation)")
+        if t.dtype != torch.float32 and t.dtype != torch.int32:
+            raise KvaeError(f"{name}: expected float32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise KvaeError(f"{name}: expected a contiguous tensor")
+        if p % 16 != 0:
+            raise KvaeError(f"{name}: base pointer must be 16-byte aligned")
         raise KvaeError(f"{name}: on {t.device}, expected {device}")
-    return c_void_p(t.data_ptr())
+    return p
 
 
 def _check(rc, what):
@@ -174,14 +177,21 @@ def mask_partials_count(dims) -> int:
     return int(lib().kvae_kf_mask_partials_count(byref(dims)))
 
 
-def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None, mask_partials=None):
-    names = ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "mus_smooth", "Sigmas_smooth", "mask_partials")
-    vals = (mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth, Sigmas_smooth, mask_partials)
+def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None, mask_partials=None,
+                a_filt=None, a_smooth=None):
+    names = ("mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "mus_smooth", "Sigmas_smooth", "mask_partials", "a_filt", "a_smooth")
+    vals = (mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth, Sigmas_smooth, mask_partials, a_filt, a_smooth)
     return KvaeStates(*[_ptr(v, k) for k, v in zip(names, vals)])
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """cudaStream_t of torch's current stream on `device` (the raw getter skips building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def filter_smooth_fwd(dims, inputs, states, A_list, B_list, C_list, info, device):

@@ -331,7 +331,8 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
           float Q1[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
           mix_Q<C>(base, al1, row0, Q1);
           sym_jitter_rows<C>(g, Q1, T1, co.diag_q ? 0.f : co.jq, Qs);
-          ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
+          unsigned clq;
+          ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q, clq) && ok_q;
           auto LQ_v = publish<MEM, L, R, N>(g, LQ, T2);
           solve_vec_l<N>(x, LQ_v, invdQ);
           if (w.with_elbo) {   // log N(x; 0, Qj) = -1/2 (n log 2pi + |LQ^-1 x|^2) - sum log diag LQ   (own-lane log terms)
@@ -348,7 +349,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
           pick_own<C>(g, x, q_own);
           KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
             // diagonal fallback: only the unclamped diagonal entries of sym(Q_t) reach L (kalman_filter.py:298-302)
-            const bool live = !co.diag_q || (row0 + r == j && dgQ[r] * dgQ[r] > 1e-6f);
+            const bool live = !co.diag_q || (row0 + r == j && !((clq >> j) & 1u));
             Qb[r][j] += live ? 0.5f * c * (q_own[r] * x[j] - Qi[r][j]) : 0.f;
           }
         } else {
@@ -451,7 +452,7 @@ KV_FN void bwd_sweep3(const Args& a, const BwdArgs& w, const float* base, const 
           const int i = row0 + r;
           const float ve = v_own[r] * eps[j];
           // (diagonal fallback: L depends on the unclamped diagonal entries of sym(Sigma_s) only)
-          const bool live_d = !co.diag_s || es.dg[r] * es.dg[r] > 1e-6f;
+          const bool live_d = !co.diag_s || !((es.clamped >> i) & 1u);
           Phi[r][j] = (j < i) ? (co.diag_s ? 0.f : ve) : ((j == i && live_d) ? 0.5f * (ve + c) : 0.f);
         }
         solve_rows_l<R, N>(Phi, Ls_v, es.invd);                       // Z = Phi Ls^-1

@@ -56,7 +56,8 @@ KV_FN int elbo_const(const Group<C::L, C::R>& g, const float* base, TileRef xbuf
     float Q[R][N], Qs[R][N], dg[R];
     copy_rows<C, N, Base<C>::ldQ>(base + Base<C>::oQ, g.row0(), Q);
     sym_jitter_rows<C>(g, Q, xbuf, co.diag_q ? 0.f : co.jq, Qs);
-    if (!chol_dist_opt<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg, co.diag_q)) bad |= KV_INFO_CHOL_Q;
+    unsigned clq;
+    if (!chol_dist_opt<C::L, R>(g, Qs, ec.LQ, ec.invdQ, dg, co.diag_q, clq)) bad |= KV_INFO_CHOL_Q;
     ec.logdetQ = logdet_half<C>(g, dg);
   }
   return bad;
@@ -69,6 +70,7 @@ template <class C> struct ElboStep {
   float dg[C::R];
   float z_own[C::R];
   float z[C::N];          // replicated sample
+  unsigned clamped;       // diagonal fallback: bit j = diagonal entry j of sym(Sigma_s) was clamped
 };
 
 // z_t from the lane's rows of Sigma_s and entries of mu_s (xbuf: [N x N] tile, vbuf: N-vector slot)
@@ -78,7 +80,7 @@ KV_FN bool elbo_sample_rows(const Group<C::L, C::R>& g, TileRef xbuf, TileRef vb
   constexpr int N = C::N, R = C::R;
   float Sj[R][N];
   sym_jitter_rows<C>(g, Ss, xbuf, co.diag_s ? 0.f : co.js, Sj);        // (:287, :293)
-  const bool ok = chol_dist_opt<C::L, R>(g, Sj, es.Ls, es.invd, es.dg, co.diag_s);
+  const bool ok = chol_dist_opt<C::L, R>(g, Sj, es.Ls, es.invd, es.dg, co.diag_s, es.clamped);
   KV_UNROLL for (int r = 0; r < R; ++r) {
     float s = 0.f;
     KV_UNROLL for (int q = 0; q < N; ++q) s = fmaf(es.Ls[r][q], eps[q], s);
@@ -172,7 +174,8 @@ KV_FN void elbo_sweep(const Args& a, const float* base, const FTiles<C>& tl, con
         float Q[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
         mix_Q<C>(base, in.al, row0, Q);
         sym_jitter_rows<C>(g, Q, tl.nn(1), co.diag_q ? 0.f : co.jq, Qs);
-        ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
+        unsigned clq;
+        ok_q = chol_dist_opt<L, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q, clq) && ok_q;
         auto LQ_v = publish<MEM, L, R, N>(g, LQ, tl.nn(2));
         solve_vec_l<N>(x, LQ_v, invdQ);
         ld = logdet_half<C>(g, dgQ);

@@ -37,6 +37,10 @@ struct Args {
   const float* dQ;   // [B,T,N,N]  nullable -> base Q
   int smooth_only;   // 1: skip the filter sweep, smooth from the filtered states already in mu_f / Sig_f
   float* mask_part;  // optional out (forward kernel): per-CTA sum of the mask, see kvae_states.mask_partials
+  // optional outs (forward kernels): the projections KVAE.impute forms afterwards (model.py:280-281, 287-288),
+  // a_filt[b,t] = C_t mu_{t|t}, a_smooth[b,t] = C_t mu_{t|T}  ([B,T,P]); nullable
+  float* a_filt;
+  float* a_smooth;
   // ELBO factorisations (kalman_filter.py:282-302 _safe_cholesky): jitter added to sym(Q_t) (the one added to sym(Sigma_s)
   // travels with the ELBO / adjoint calls) and the final rung of the reference's ladder, L = diag(sqrt(clamp(diag, 1e-6))),
   // selected per matrix family: bit 0 = Sigma_smooth, bit 1 = Q
@@ -216,6 +220,17 @@ template <class C> KV_FN void mix_Ct(const float* base, const float (&al)[C::K],
 template <class C> KV_FN void mix_Q(const float* base, const float (&al)[C::K], int row0, float (&Q)[C::R][C::N]) {
   if constexpr (C::QPM) mix_one<C, C::N, Base<C>::ldQ>(base + Base<C>::oQ, C::K, al, row0, Q);
   else copy_rows<C, C::N, Base<C>::ldQ>(base + Base<C>::oQ, row0, Q);
+}
+
+// out[q] = sum_j C_t[q][j] v[j] from the lane's rows of C_t^T and its entries of v (all lanes of the group take part)
+template <class C>
+KV_FN void project_obs(const Group<C::L, C::R>& g, const float (&Ct)[C::R][C::P], const float (&v_own)[C::R], float (&out)[C::P]) {
+  KV_UNROLL for (int q = 0; q < C::P; ++q) {
+    float s = 0.f;
+    KV_UNROLL for (int r = 0; r < C::R; ++r) s = fmaf(Ct[r][q], v_own[r], s);
+    out[q] = s;
+  }
+  g.allreduce(out);
 }
 
 // explicit-matrix variants (forward kernels): read the step's rows from dense per-step tensors when given
@@ -420,6 +435,11 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
     const float (&Sp)[R][N] = fo.Sp;
     const float (&Sf)[R][N] = fo.Sf;
 
+    if (a.a_filt) {   // C_t mu_{t|t} (model.py:287-288): C_t^T rows are in registers
+      float af[P];
+      project_obs<C>(g, Ct, muf, af);
+      if (active && g.lane == 0) store_row<P>(a.a_filt + bt * P, af);
+    }
     if (active) {
       KV_UNROLL for (int r = 0; r < R; ++r) {
         store_row<N>(a.Sig_p + (bt * N + row0 + r) * N, Sp[r]);
@@ -582,6 +602,12 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     }
     float A1[R][N];
     get_A<C>(a, base, al1, row0, bt + 1, A1);
+    if (a.a_smooth) {   // C_{t+1} mu_{t+1|T} (model.py:280-281): alpha_{t+1} and the smoothed mean at t+1 are in hand here
+      float Ct1[R][C::P], as[C::P];
+      get_Ct<C>(a, base, al1, row0, bt + 1, Ct1);
+      project_obs<C>(g, Ct1, mus, as);
+      if (active && g.lane == 0) store_row<C::P>(a.a_smooth + (bt + 1) * C::P, as);
+    }
     // (issued AFTER the mixing loads: directly in front of them the prefetch shared a scoreboard with the LDS of the
     //  mixing, so the first mixing FMA waited for the whole L2 round trip -- 40 % of this kernel's stall samples)
     if (staged && ((t + 1) & 3) == 0 && t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
@@ -591,6 +617,15 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
       KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Sig[r]);
       store_row<R>(a.mu_s + bt * N + row0, mus);
     }
+  }
+  if (a.a_smooth) {   // t = 0 (alpha_0 was never needed by the smoother itself)
+    const long bt0 = (long)b * T;
+    float al0[C::K], Ct0[R][C::P], as[C::P];
+    if (a.alpha) load_row<C::K>(a.alpha + bt0 * C::K, al0);
+    else { KV_UNROLL for (int k = 0; k < C::K; ++k) al0[k] = 0.f; }
+    get_Ct<C>(a, base, al0, row0, bt0, Ct0);
+    project_obs<C>(g, Ct0, mus, as);
+    if (active && g.lane == 0) store_row<C::P>(a.a_smooth + bt0 * C::P, as);
   }
   if (!ok && active) kv_info_or(a.info, KV_INFO_PIVOT);
 }

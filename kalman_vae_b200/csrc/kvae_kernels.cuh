@@ -126,11 +126,9 @@ template <class C> int launch_fwd_lstm(const Args& a, const BasePtrs& bp, const 
   (void)cudaGetLastError();
   constexpr int GPB = TPB<C> / C::L;
   const size_t sm = smem_bytes_lstm<C>();
-  static bool attr_set = false;
-  if (sm > 48 * 1024 && !attr_set) {
+  if (sm > 48 * 1024) {   // per DEVICE attribute: set on every launch (cheap, idempotent) so that a second GPU of the process works too
     cudaError_t e = cudaFuncSetAttribute(k_filter_lstm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int grid = (a.B + GPB - 1) / GPB;
   constexpr int tpb = TPB<C>;
@@ -144,11 +142,9 @@ template <class C> int launch_fwd(const Args& a, const BasePtrs& bp, int smooth,
   (void)cudaGetLastError();  // do not inherit a stale (non-sticky) error from an earlier call
   constexpr int GPB = TPB<C> / C::L;
   const size_t sm = smem_bytes<C>();
-  static bool attr_set = false;  // benign race: idempotent
-  if (sm > 48 * 1024 && !attr_set) {
+  if (sm > 48 * 1024) {   // per DEVICE attribute: set on every launch (cheap, idempotent) so that a second GPU of the process works too
     cudaError_t e = cudaFuncSetAttribute(k_filter_smooth<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int grid = (a.B + GPB - 1) / GPB;
   constexpr int tpb = TPB<C>;
@@ -258,11 +254,9 @@ template <class C> size_t elbo_ws_bytes(int B, int T) {
 template <class C> int launch_elbo(const Args& a, const BasePtrs& bp, float jitter, float* terms, void* ws, cudaStream_t s) {
   constexpr int GPB = TPB<C> / C::L;
   const size_t sm = smem_bytes_elbo<C>();
-  static bool attr_set = false;
-  if (sm > 48 * 1024 && !attr_set) {
+  if (sm > 48 * 1024) {   // per DEVICE attribute: set on every launch (cheap, idempotent) so that a second GPU of the process works too
     cudaError_t e = cudaFuncSetAttribute(k_elbo<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const ChunkMap cm = make_chunks(a.B, a.T, C::L);
   const int grid = chunk_grid<C>(a.B, cm.chunks);
@@ -614,12 +608,10 @@ int launch_bwd(const Args& a, BwdArgs w, const BasePtrs& bp, const float* g_elbo
   constexpr int GPB = TPBB<C> / C::L;
   using GA = GradAcc<C>;
   const size_t sm = sizeof(float) * smem_floats_bwd<C>();
-  static bool attr_set = false;
   (void)cudaGetLastError();
-  if (sm > 48 * 1024 && !attr_set) {
+  if (sm > 48 * 1024) {   // per DEVICE attribute: set on every launch (cheap, idempotent) so that a second GPU of the process works too
     cudaError_t e = cudaFuncSetAttribute(k_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const size_t BT = (size_t)a.B * a.T;
   const size_t nn = align256(sizeof(float) * BT * C::N * C::N);

@@ -389,13 +389,15 @@ KV_FN bool chol_dist(const Group<L, R>& g, const float (&a)[R][L * R], float (&l
 // L = diag(sqrt(clamp(diag(a), 1e-6))) (a: symmetrised, no jitter).  Never fails in that mode.
 template <int L, int R>
 KV_FN bool chol_dist_opt(const Group<L, R>& g, const float (&a)[R][L * R], float (&l)[R][L * R], float (&invd)[L * R],
-                         float (&dg_own)[R], int diag) {
+                         float (&dg_own)[R], int diag, unsigned& clamped) {
+  clamped = 0u;   // bit j: diagonal entry j was clamped (no gradient flows through it); replicated over the group
   if (!diag) return chol_dist<L, R>(g, a, l, invd, dg_own);
   constexpr int N = L * R;
   KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) l[r][j] = 0.f;
   KV_UNROLL for (int j = 0; j < N; ++j) {
     const int owner = j / R, jr = j % R;
     float d = g.bcast(a[jr][j], owner);
+    if (!(d > 1e-6f)) clamped |= 1u << j;
     d = sqrtf(d > 1e-6f ? d : 1e-6f);
     invd[j] = 1.0f / d;
     KV_UNROLL for (int r = 0; r < R; ++r) {

@@ -334,6 +334,11 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
         if (active) {   // 16-byte rows: plain stores (see the file header)
           store_row<N>(a.mu_p + ((long)b * T + t) * N, fo.mup);
           store_row<N>(a.mu_f + ((long)b * T + t) * N, fo.muf);
+          if (a.a_filt) {   // C_t mu_{t|t} (model.py:287-288)
+            float af[P];
+            project_obs<C>(g, Ct, fo.muf, af);
+            store_row<P>(a.a_filt + ((long)b * T + t) * P, af);
+          }
         }
         tma::fence_async();
         __syncwarp();
@@ -399,6 +404,12 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
       KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = al_pf[k];
       float A1[R][N];
       mix_A<C>(base, al1, 0, A1);
+      if (a.a_smooth && active) {   // C_{t+1} mu_{t+1|T} (model.py:280-281): both are in hand at the top of step t
+        float Ct1[R][P], as[P];
+        mix_Ct<C>(base, al1, 0, Ct1);
+        project_obs<C>(g, Ct1, mus, as);
+        store_row<P>(a.a_smooth + ((long)b * T + t + 1) * P, as);
+      }
       if (t > 0) {
         load_smooth_in<C>(a, bt - 1, 0, pf);
         load_row<K>(a.alpha + bt * K, al_pf);
@@ -414,6 +425,13 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
         tma::store3d(&mp.Sig_s, 0, t, b0, tma::s32(tSs), pol_ef);
         tma::commit();
       }
+    }
+    if (a.a_smooth && active) {   // t = 0
+      float al0[K], Ct0[R][P], as[P];
+      load_row<K>(a.alpha + (long)b * T * K, al0);
+      mix_Ct<C>(base, al0, 0, Ct0);
+      project_obs<C>(g, Ct0, mus, as);
+      store_row<P>(a.a_smooth + (long)b * T * P, as);
     }
   }
   if (warp_on) tma::wait_all0();   // the staging tiles must outlive their stores

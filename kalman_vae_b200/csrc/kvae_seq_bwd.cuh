@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
           float Q1[R][N], Qs[R][N], LQ[R][N], invdQ[N], dgQ[R];
           mix_Q<C>(base, in1.al, 0, Q1);
           sym_jitter_rows<C>(g, Q1, NT, co.diag_q ? 0.f : co.jq, Qs);
-          ok_q = chol_dist_opt<1, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q) && ok_q;
+          unsigned clq;
+          ok_q = chol_dist_opt<1, R>(g, Qs, LQ, invdQ, dgQ, co.diag_q, clq) && ok_q;
           RegView<N, N> LQ_v{LQ};
           solve_vec_l<N>(x, LQ_v, invdQ);
           if (w.with_elbo) {
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
           KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) Qi[r][j] = (r == j) ? 1.f : 0.f;
           solve_rows_llt<R, N>(Qi, LQ_v, invdQ);
           KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
-            const bool live = !co.diag_q || (r == j && dgQ[r] * dgQ[r] > 1e-6f);   // diagonal fallback: see kvae_bwd.cuh
+            const bool live = !co.diag_q || (r == j && !((clq >> j) & 1u));   // diagonal fallback: see kvae_bwd.cuh
             Qb[r][j] += live ? 0.5f * c * (x[r] * x[j] - Qi[r][j]) : 0.f;
           }
         } else {
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(64) k_seq_bwd(Args a, BwdArgs w, BasePtrs bp, 
         float Phi[R][N];
         KV_UNROLL for (int r = 0; r < R; ++r) KV_UNROLL for (int j = 0; j < N; ++j) {
           const float ve = v_own[r] * eps_cur[j];
-          const bool live_d = !co.diag_s || es.dg[r] * es.dg[r] > 1e-6f;
+          const bool live_d = !co.diag_s || !((es.clamped >> r) & 1u);
           Phi[r][j] = (j < r) ? (co.diag_s ? 0.f : ve) : ((j == r && live_d) ? 0.5f * (ve + c) : 0.f);
         }
         solve_rows_l<R, N>(Phi, Ls_v, es.invd);

@@ -30,6 +30,7 @@ Args make_args(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st,
   a.dA = in.A_dense; a.dB = in.B_dense; a.dC = in.C_dense; a.dQ = in.Q_dense;
   a.smooth_only = (d.flags & KVAE_FLAG_SMOOTH_ONLY) ? 1 : 0;
   a.mask_part = nullptr;
+  a.a_filt = st.a_filt; a.a_smooth = st.a_smooth;
   a.jitter_q = 1e-6f;
   a.chol_diag = 0;
   a.info = info;

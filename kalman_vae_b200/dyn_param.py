@@ -95,18 +95,23 @@ class PrecomputedWeights(nn.Module):
         self.alpha = None
         self.state_seq = None
         self.lstm_state = None
+        self._zeros = None
 
     def set_weights(self, alpha):
-        self.alpha = alpha
+        object.__setattr__(self, "alpha", alpha)      # plain per-call tensors: skip nn.Module's attribute bookkeeping
 
     def reset_state(self):
-        self.state_seq = None
+        object.__setattr__(self, "state_seq", None)
 
     def compute_weights(self, a_seq, is_training=True):
         B, T, _ = a_seq.shape
-        self.state_seq = self.alpha
-        self.log_qseq = torch.zeros(B, T, device=a_seq.device, dtype=a_seq.dtype)
-        self.log_pseq = torch.zeros(B, T, device=a_seq.device, dtype=a_seq.dtype)
+        object.__setattr__(self, "state_seq", self.alpha)
+        z = self._zeros
+        if z is None or z.shape != (B, T) or z.device != a_seq.device or z.dtype != a_seq.dtype:
+            z = torch.zeros(B, T, device=a_seq.device, dtype=a_seq.dtype)
+            object.__setattr__(self, "_zeros", z)
+        object.__setattr__(self, "log_qseq", z)      # no regime chain here: log q = log p = 0
+        object.__setattr__(self, "log_pseq", z)
         return self.alpha
 
     def elbo_terms(self):

@@ -149,19 +149,25 @@ class States:
     mus_smooth: Optional[torch.Tensor] = None
     Sigmas_smooth: Optional[torch.Tensor] = None
     mask_partials: Optional[torch.Tensor] = None   # per-CTA mask sums of the forward launch (kvae_states.mask_partials)
+    a_filt: Optional[torch.Tensor] = None          # [B,T,p] C_t mu_{t|t}  (optional forward output)
+    a_smooth: Optional[torch.Tensor] = None        # [B,T,p] C_t mu_{t|T}  (optional forward output)
 
     def c_struct(self):
         return capi.make_states(self.mus_filt, self.Sigmas_filt, self.mus_pred, self.Sigmas_pred,
-                                self.mus_smooth, self.Sigmas_smooth, self.mask_partials)
+                                self.mus_smooth, self.Sigmas_smooth, self.mask_partials, self.a_filt, self.a_smooth)
 
 
-def smooth_fwd(pb: Problem, smooth=True, lists=True):
-    """Runs the forward recursion; returns (States, A_list, B_list, C_list)."""
+def smooth_fwd(pb: Problem, smooth=True, lists=True, projections=False):
+    """Runs the forward recursion; returns (States, A_list, B_list, C_list).  projections: the launch also emits
+    States.a_filt = C_t mu_{t|t} and (smooth) States.a_smooth = C_t mu_{t|T}."""
     B, T, n, p, m, K = pb.shape
     dev = pb.Y.device
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     st = States(e(B, T, n, 1), e(B, T, n, n), e(B, T, n, 1), e(B, T, n, n),
                 e(B, T, n, 1) if smooth else None, e(B, T, n, n) if smooth else None)
+    if projections:
+        st.a_filt = e(B, T, p)
+        st.a_smooth = e(B, T, p) if smooth else None
     if smooth and pb.dense is None and not (pb.dims.flags & capi.FLAG_SMOOTH_ONLY):
         st.mask_partials = e(max(mask_partials_count(pb.dims), 4))
     A_list = e(B, T, n, n) if lists else None

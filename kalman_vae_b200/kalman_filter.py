@@ -65,6 +65,7 @@ class KalmanFilter(nn.Module):
         self.strict = False             # True: verify (host syncs) that elbo() sees the same y / u / mask VALUES as smooth()
         self._prep_cache = {}
         self._deferred = []             # [(event, pinned int32 word, kind)] device-side checks read one call late
+        self._ring = None
 
     # ------------------------------------------------------------------ helpers
     def _mask(self, mask, B, T, ref):
@@ -78,13 +79,17 @@ class KalmanFilter(nn.Module):
     # ------------------------------------------------------------------ deferred device-side checks
     def _defer(self, flag, kind):
         """Queues a device int32 `flag` (non-zero = failure) for a look at the start of the next public call."""
-        host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        host.copy_(flag.reshape(1).to(torch.int32), non_blocking=True)
+        if self._ring is None:     # pinned words are allocated ONCE (cudaHostAlloc synchronises the device)
+            self._ring = torch.zeros(16, dtype=torch.int32).pin_memory()
+            self._ring_i = 0
+        if len(self._deferred) >= 8:      # never let the queue catch up with the ring: wait for the oldest entry
+            self._poll_deferred(block_oldest=True)
+        host = self._ring[self._ring_i:self._ring_i + 1]
+        self._ring_i = (self._ring_i + 1) % 16
+        host.copy_(flag if flag.dtype == torch.int32 else flag.reshape(1).to(torch.int32), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(flag.device))
         self._deferred.append((ev, host, kind))
-        if len(self._deferred) > 8:      # never let the queue grow: wait for the oldest entry
-            self._poll_deferred(block_oldest=True)
 
     def _poll_deferred(self, block_oldest=False):
         keep = []
@@ -327,8 +332,8 @@ class KalmanFilter(nn.Module):
     def impute_observations(self, Y, U, mask=None):
         """The Kalman part of KVAE.impute (model.py:267-288) without materialising the per-step
         matrices: smooth, then  a_imputed = C_t mu_{t|T},  a_filtered = C_t mu_{t|t}  straight from the mixture weights
-        (`(C_list @ mus).squeeze(-1)` in the reference).  The forward launch skips A_list / B_list / C_list (160 of its 440
-        output bytes per sequence-step at the KVAE shapes).  Returns (a_imputed [B,T,p], a_filtered [B,T,p],
+        (`(C_list @ mus).squeeze(-1)` in the reference): the filter / smoother sweeps emit C_t mu themselves
+        (kvae_states.a_filt / a_smooth) and skip A_list / B_list / C_list (160 of the 440 output bytes per sequence-step).  Returns (a_imputed [B,T,p], a_filtered [B,T,p],
         mus_smooth [B,T,n,1], mus_filt [B,T,n,1]).  Forward only, like the reference's impute()."""
         B, T, _ = Y.shape
         mask_t = self._mask(mask, B, T, Y)
@@ -340,16 +345,15 @@ class KalmanFilter(nn.Module):
         else:
             alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
             pb = self._problem(Y, U, mask_t, alpha, A, Bm, C, Q, qpm, csh)
-            st, _, _, _ = F.smooth_fwd(pb, smooth=True, lists=False)
-            ms, mf = st.mus_smooth, st.mus_filt
+            # the sweeps emit the two projections themselves (kvae_states.a_filt / a_smooth): no list tensors, no GEMM
+            st, _, _, _ = F.smooth_fwd(pb, smooth=True, lists=False, projections=True)
+            return st.a_smooth, st.a_filt, st.mus_smooth, st.mus_filt
+        # (lstm dynamics in the filter loop: the fused LSTM launch does not emit the projections; two small GEMMs)
         Cp = dyn.C.detach().to(torch.float32)
-        if csh:
-            proj = lambda mu: mu.squeeze(-1) @ Cp[0].T
-        else:   # sum_k alpha_k (C_k mu): one GEMM [B*T,n] x [n,K*p] and a weighted sum over the modes
-            K, p, n = Cp.shape
-            Cflat = Cp.reshape(K * p, n).T
-            al = alpha.to(torch.float32).unsqueeze(-1)
-            proj = lambda mu: ((mu.squeeze(-1) @ Cflat).view(B, T, K, p) * al).sum(2)
+        K, p, n = Cp.shape
+        Cflat = Cp.reshape(K * p, n).T
+        al = alpha.to(torch.float32).unsqueeze(-1)
+        proj = lambda mu: ((mu.squeeze(-1) @ Cflat).view(B, T, K, p) * al).sum(2)
         return proj(ms), proj(mf), ms, mf
 
     def elbo(self, mu_t_T, Sigma_t_T, y_t, u_t, A_list, B_list, C_list, Q_list=None, mask=None):
@@ -400,7 +404,7 @@ class KalmanFilter(nn.Module):
                 info.zero_()
             val = run(1e-6)
             if self.check_info:
-                self._defer(info.clone(), "chol")
+                self._defer(info, "chol")   # stream-ordered copy: later launches cannot overtake it
             return val
         # the reference's _safe_cholesky ladder (kalman_filter.py:282-302), one ladder per factorised family as there:
         # any failing matrix bumps the jitter of its family 10x for the WHOLE batch (:295-296); after five failed

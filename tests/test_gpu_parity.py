@@ -190,3 +190,20 @@ def test_full_size_cfg2_against_oracle():
             e32, e64, floor = check_close(f"cfg2.{k}", v, r32[k], r64[k])
             print(f"cfg2 full size {k}: e32 {e32:.1e} e64 {e64:.1e} floor {floor:.1e}")
     print(f"cfg2 full size: worst forward error vs reference-order fp32 {worst:.1e}")
+
+
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_switch", "kalman_zero_mask", "kalman_T1", "kalman_n8"])
+def test_projections_emitted_by_the_sweeps(name):
+    """a_filt = C_t mu_{t|t} and a_smooth = C_t mu_{t|T} written by the filter / smoother sweeps
+    (kvae_states.a_filt / a_smooth) equal the reference's `(C_list @ mus).squeeze(-1)` (model.py:280-281, 287-288),
+    every lane count (lanes = 1 with T % 4 == 0: the thread-per-sequence kernel)."""
+    dev = torch.device("cuda:0")
+    case, _, r32, r64 = load_golden(name)
+    want = {k: (r[("C_list")].double() @ r[m].double()).squeeze(-1) for k, m in (("a_filt", "mus_filt"), ("a_smooth", "mus_smooth"))
+            for r in (r64,)}
+    want32 = {k: (r32["C_list"] @ r32[m]).squeeze(-1) for k, m in (("a_filt", "mus_filt"), ("a_smooth", "mus_smooth"))}
+    for lanes in lanes_for(case["A"].shape[-1]):
+        pb, _ = problem(case, lanes, dev)
+        st, *_ = F.smooth_fwd(pb, smooth=True, lists=False, projections=True)
+        for k in ("a_filt", "a_smooth"):
+            check_close(f"{name}.L{lanes}.{k}", getattr(st, k), want32[k], want[k], rtol=2e-5)

@@ -31,4 +31,4 @@ print(f"host enqueue time per step {t_host/500*1e3:.3f} ms; incl. final sync {t_
 pr = cProfile.Profile(); pr.enable()
 for _ in range(300): step()
 pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
