@@ -282,6 +282,30 @@ int kvae_regime_sample_bwd(const kvae_regime_dims* d, const float* logits, const
                            const float* g_logq, const float* g_logp, float* d_logits, float* d_init,
                            int device, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * VAE-side reductions feeding the same loss:  vae_loss  kvae/vae/losses.py:62-111 and
+ * KVAE.reparameterize  kvae/model/model.py:81-84.  Frames x [frames, pixels] (= [B*T, C*H*W]), reconstruction means /
+ * logits x_mu (same shape), latents a, a_mu, a_var [frames, a_dim], mask [frames] or NULL (= ones).
+ *   out8: [0] vae_elbo = scale_reconstruction * recon + beta * reg   [1] recon = sum(m log p(x|a)) / denom
+ *         [2] reg = (sum m log p(a) - sum m log q(a|x)) / denom       [3] 1/denom, denom = max(sum m, 1)   [4..7] raw sums
+ *   bernoulli != 0: log p(x|a) = -BCEWithLogits(x_mu, x) (x_var ignored); else Gaussian with the scalar variance x_var.
+ * The backward entry returns the gradient of g3[0]*vae_elbo + g3[1]*recon + g3[2]*reg (g3: 3 device floats) with
+ * respect to x_mu, a, a_mu, a_var.  workspace: kvae_vae_loss_workspace_bytes(d) bytes (forward only). */
+typedef struct kvae_vae_dims {
+  int32_t frames, pixels, a_dim, bernoulli;
+  float x_var, scale_reconstruction, beta;
+} kvae_vae_dims;
+const char* kvae_vae_last_error(void);
+size_t kvae_vae_loss_workspace_bytes(const kvae_vae_dims* d);
+int kvae_vae_loss_fwd(const kvae_vae_dims* d, const float* x, const float* x_mu, const float* a, const float* a_mu,
+                      const float* a_var, const float* mask, float* out8, void* workspace, int device, void* stream);
+int kvae_vae_loss_bwd(const kvae_vae_dims* d, const float* x, const float* x_mu, const float* a, const float* a_mu,
+                      const float* a_var, const float* mask, const float* g3, const float* out8, float* d_x_mu, float* d_a,
+                      float* d_a_mu, float* d_a_var, int device, void* stream);
+/* a = mu + eps * sqrt(var + 1e-6); backward: d_mu = g (the caller's own), d_var = g * eps / (2 sqrt(var + 1e-6)) */
+int kvae_vae_reparam_fwd(const float* mu, const float* var, const float* eps, long n, float* a, int device, void* stream);
+int kvae_vae_reparam_bwd(const float* var, const float* eps, const float* g, long n, float* d_var, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ def build(force=False, verbose=False):
     jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_regime.cu"), "-o", o], o))
     o = os.path.join(OBJ, "dp.o")
     jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_dp.cu"), "-o", o], o))
+    o = os.path.join(OBJ, "vae.o")
+    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_vae.cu"), "-o", o], o))
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
     if verbose:

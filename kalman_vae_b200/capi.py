@@ -119,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "kvae_kf_bwd_workspace_bytes", "kvae_kf_bwd", "kvae_kf_elbo_fwd_ex", "kvae_kf_bwd_ex",
     "kvae_regime_last_error", "kvae_regime_supported", "kvae_regime_sample_fwd", "kvae_regime_sample_bwd",
     "kvae_dp_last_error", "kvae_dp_handle_bytes", "kvae_dp_create", "kvae_dp_connect", "kvae_dp_destroy", "kvae_dp_finalize", "kvae_kf_bwd_dp",
+    "kvae_vae_last_error", "kvae_vae_loss_workspace_bytes", "kvae_vae_loss_fwd", "kvae_vae_loss_bwd", "kvae_vae_reparam_fwd", "kvae_vae_reparam_bwd",
 ]
 
 

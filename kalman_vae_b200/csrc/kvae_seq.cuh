@@ -118,6 +118,7 @@ __device__ __forceinline__ void store3d(const CUtensorMap* m, int c0, int c1, in
 #endif
 __device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
 __device__ __forceinline__ void wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes of this thread to shared memory become visible to the async proxy (TMA store source)
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -170,12 +171,16 @@ __host__ __device__ constexpr int kv_align_up(int x, int a) { return (x + a - 1)
 
 // Shared-memory plan of one warp of k_seq_fwd (bytes).  Swizzled tiles need their base aligned to the swizzle period
 // (512 bytes for SWIZZLE_64B, 256 for SWIZZLE_32B); every tile is 512-byte aligned.  Sweep 2 reuses sweep 1's region.
+// sets of output staging tiles per warp: with two, step t+1 fills its tiles while the TMA engine still reads step t's
+#ifndef KV_SEQ_OUT_BUFS
+#define KV_SEQ_OUT_BUFS 2
+#endif
 template <class C> struct SeqFwdPlan {
   static constexpr int P = C::P, K = C::K, M = C::M;
   using TM = RowTile<4>;    // Sigma / A / B rows
   using TC = RowTile<P>;    // C rows ([P][4])
-  // output tiles of one step (sweep 2 reuses oSp for Sigma_s), then the input chunk (single buffer, re-armed one step
-  // ahead of its first use)
+  // output tiles of one step (sweep 2 reuses oSp for Sigma_s), then two input-chunk buffers (the next chunk is requested
+  // three steps before its first use; the 78 KB floor per CTA leaves room for them)
   static constexpr int oSp = 0, oSf = oSp + TM::bytes, oA = oSf + TM::bytes, oB = oA + TM::bytes;
   static constexpr int oC = oB + TM::bytes;
   static constexpr int in_Y = 0, in_U = in_Y + 32 * 4 * P * 4, in_al = in_U + 32 * 4 * M * 4, in_m = in_al + 32 * 4 * K * 4;
@@ -183,8 +188,9 @@ template <class C> struct SeqFwdPlan {
   static __host__ __device__ constexpr uint32_t in_tx(bool has_u, bool has_m) {
     return 32u * 4 * P * 4 + (has_u ? 32u * 4 * M * 4 : 0u) + 32u * 4 * K * 4 + (has_m ? 32u * 4 * 4 : 0u);
   }
-  static constexpr int oIn = kv_align_up(oC + TC::bytes, 512);
-  static constexpr int warp_bytes = kv_align_up(oIn + in_bytes, 512);
+  static constexpr int out_bytes = kv_align_up(oC + TC::bytes, 512);
+  static constexpr int oIn = KV_SEQ_OUT_BUFS * out_bytes;
+  static constexpr int warp_bytes = kv_align_up(oIn + 2 * in_bytes, 512);   // two input-chunk buffers
 };
 
 #ifndef KV_SEQ_MAXWARPS
@@ -193,7 +199,7 @@ template <class C> struct SeqFwdPlan {
 template <class C> constexpr size_t seq_fwd_smem(int warps) {
   return 512 + (size_t)kv_align_up((int)sizeof(float) * Base<C>::total, 512) + (size_t)warps * SeqFwdPlan<C>::warp_bytes;
 }
-// warps per CTA.  A warp stages 14 KB; four-warp CTAs (three per SM by registers); small batches use two-warp CTAs so
+// warps per CTA.  A warp stages 19 KB; four-warp CTAs, two per SM (see seq_smem_floor); small batches use two-warp CTAs so
 // that the few warps spread over all SMs and land on distinct schedulers.
 inline int seq_env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 inline int seq_warps_per_cta(int B) {
@@ -237,7 +243,7 @@ __device__ __forceinline__ void seq_read_step(const unsigned char* in, int lane,
 }
 
 template <class C>
-__global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, BasePtrs bp, const __grid_constant__ SeqFwdMaps mp,
+__global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 2) k_seq_fwd(Args a, BasePtrs bp, const __grid_constant__ SeqFwdMaps mp,
                                                                   int smooth) {
   static_assert(C::L == 1 && C::N == 4 && C::M == 4, "thread-per-sequence kernels: z_dim = u_dim = 4");
   constexpr int N = C::N, P = C::P, M = C::M, K = C::K, R = C::R;
@@ -260,7 +266,6 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
   const bool has_u = a.U != nullptr, has_m = a.mask != nullptr;
   const Group<1, R> g{0, 0xffffffffu};
   const FTiles<C> tl{base, 0};   // L = 1: never dereferenced (views alias registers)
-  const uint32_t bar_in0 = tma::s32(&bars[warp][0]);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) tma::bar_init(tma::s32(&bars[warp][i]), 1);
@@ -278,43 +283,47 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
     load_row<N>(base + Base<C>::oMu0, mu);
     if (a.Sig_init && active) { KV_UNROLL for (int r = 0; r < R; ++r) load_row<N>(a.Sig_init + ((long)b * N + r) * N, Sig[r]); }
     if (a.mu_init && active) load_row<N>(a.mu_init + (long)b * N, mu);
-    SeqBar bar_in{bar_in0, 0u};
-    unsigned char* ib = wsm + PL::oIn;
-    auto issue_in = [&](int c) {   // elected lane: the four input streams of chunk c
-      tma::bar_expect(bar_in.addr, PL::in_tx(has_u, has_m));
-      tma::load2d(tma::s32(ib + PL::in_Y), &mp.Y, 4 * c * P, b0, bar_in.addr, pol_ef);
-      if (has_u) tma::load2d(tma::s32(ib + PL::in_U), &mp.U, 4 * c * M, b0, bar_in.addr, pol_ef);
-      tma::load2d(tma::s32(ib + PL::in_al), &mp.alpha, 4 * c * K, b0, bar_in.addr, smooth ? pol_el : pol_ef);
-      if (has_m) tma::load2d(tma::s32(ib + PL::in_m), &mp.mask, 4 * c, b0, bar_in.addr, pol_ef);
+    SeqBar bar_in[2] = {{tma::s32(&bars[warp][0]), 0u}, {tma::s32(&bars[warp][1]), 0u}};
+    unsigned char* ib0 = wsm + PL::oIn;
+    auto issue_in = [&](int c) {   // elected lane: the four input streams of chunk c into buffer c & 1
+      unsigned char* ib = ib0 + (c & 1) * PL::in_bytes;
+      const uint32_t bar = bar_in[c & 1].addr;
+      tma::bar_expect(bar, PL::in_tx(has_u, has_m));
+      tma::load2d(tma::s32(ib + PL::in_Y), &mp.Y, 4 * c * P, b0, bar, pol_ef);
+      if (has_u) tma::load2d(tma::s32(ib + PL::in_U), &mp.U, 4 * c * M, b0, bar, pol_ef);
+      tma::load2d(tma::s32(ib + PL::in_al), &mp.alpha, 4 * c * K, b0, bar, smooth ? pol_el : pol_ef);
+      if (has_m) tma::load2d(tma::s32(ib + PL::in_m), &mp.mask, 4 * c, b0, bar, pol_ef);
     };
     if (tma::elect_one()) issue_in(0);
-    float* tSp = reinterpret_cast<float*>(wsm + PL::oSp);
-    float* tSf = reinterpret_cast<float*>(wsm + PL::oSf);
-    float* tA = reinterpret_cast<float*>(wsm + PL::oA);
-    float* tB = reinterpret_cast<float*>(wsm + PL::oB);
-    float* tC = reinterpret_cast<float*>(wsm + PL::oC);
-    bar_in.wait();
+    bar_in[0].wait();
     StepIn<C> cur;
-    seq_read_step<C>(ib, lane, 0, has_u, has_m, cur);
+    seq_read_step<C>(ib0, lane, 0, has_u, has_m, cur);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       {
-        // inputs of step t+1 (they become `cur` of the next iteration); the chunk buffer is re-armed with the next
-        // chunk as soon as its last step has been read, i.e. one whole step before that chunk's first use
+        // inputs of step t+1 (they become `cur` of the next iteration).  Chunk c+1 is requested at the first step of
+        // chunk c (its buffer held chunk c-1, whose last step was read two steps ago): three steps before its first use
         StepIn<C> nxt = cur;
         if (t + 1 < T) {
-          if (((t + 1) & 3) == 0) bar_in.wait();
-          seq_read_step<C>(ib, lane, (t + 1) & 3, has_u, has_m, nxt);
+          const int c1 = (t + 1) >> 2;
+          if (((t + 1) & 3) == 0) bar_in[c1 & 1].wait();
+          seq_read_step<C>(ib0 + (c1 & 1) * PL::in_bytes, lane, (t + 1) & 3, has_u, has_m, nxt);
         }
         __syncwarp();
-        if (((t + 1) & 3) == 3 && t + 2 < T && tma::elect_one()) issue_in((t + 2) >> 2);
+        if ((t & 3) == 0 && t + 4 < T && tma::elect_one()) issue_in((t >> 2) + 1);
         float A[R][N], Bm[R][M], Ct[R][P], Q[R][N];
         mix_A<C>(base, cur.al, 0, A);
         mix_B<C>(base, cur.al, 0, Bm);
         mix_Ct<C>(base, cur.al, 0, Ct);
         mix_Q<C>(base, cur.al, 0, Q);
-        // the staging tiles are free once the previous step's stores have READ them
-        tma::wait_read0();   // all lanes: only the electing lane has groups pending
+        // this step's set of staging tiles is free once the stores that last used it have READ it
+        unsigned char* ot = wsm + (KV_SEQ_OUT_BUFS == 2 ? (t & 1) * PL::out_bytes : 0);
+        float* tSp = reinterpret_cast<float*>(ot + PL::oSp);
+        float* tSf = reinterpret_cast<float*>(ot + PL::oSf);
+        float* tA = reinterpret_cast<float*>(ot + PL::oA);
+        float* tB = reinterpret_cast<float*>(ot + PL::oB);
+        float* tC = reinterpret_cast<float*>(ot + PL::oC);
+        if (KV_SEQ_OUT_BUFS == 2) tma::wait_read1(); else tma::wait_read0();   // all lanes: only the electing lane has groups pending
         __syncwarp();
         if (a.A_list) TM::st_mat(tA, lane, A);
         if (a.B_list) TM::st_mat(tB, lane, Bm);
@@ -376,7 +385,9 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
     // sweep 1's TMA stores must have LANDED: the smoother reads Sigma_f / Sigma_p back with ordinary loads
     tma::wait_all0();
     __syncwarp();
-    float* tSs = reinterpret_cast<float*>(wsm + PL::oSp);
+    float* tSs0 = reinterpret_cast<float*>(wsm + PL::oSp);
+    float* tSs1 = reinterpret_cast<float*>(wsm + (KV_SEQ_OUT_BUFS == 2 ? PL::oSf : PL::oSp));
+    float* tSs = tSs1;
     const int bl = active ? b : a.B - 1;   // tail lanes re-read the last sequence and store nothing
     // t = T-1: copied, not symmetrised (kalman_filter.py:251-256)
     TM::st_mat(tSs, lane, Sig);
@@ -387,21 +398,41 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
       tma::store3d(&mp.Sig_s, 0, T - 1, b0, tma::s32(tSs), pol_ef);
       tma::commit();
     }
-    SmoothIn<C> pf;          // states of the NEXT iteration, fetched one step ahead
-    float al_pf[K];          // alpha_{t+1} of the next iteration
-    if (T >= 2) {
-      load_smooth_in<C>(a, (long)bl * T + (T - 2), 0, pf);
-      load_row<K>(a.alpha + ((long)bl * T + (T - 1)) * K, al_pf);
-    }
-#pragma unroll 1
-    for (int t = T - 2; t >= 0; --t) {
+    // What an iteration needs -- Sigma_f(t), Sigma_p(t+1), mu_f(t), mu_p(t+1), alpha_{t+1} -- is requested TWO iterations
+    // ahead (with the machine full one iteration does not cover the HBM latency: 21 % of this kernel's stall samples sat on
+    // the first use of a one-step prefetch).  The two engines share the work: the 64-byte covariance rows come through the
+    // TMA engine into a ring of three [Sigma_f | Sigma_p] tile pairs (mbarrier per slot; the ring reuses sweep 1's
+    // staging area), the 16-byte mean rows and alpha through plain vector loads into two alternating register sets.
+    // (All of it through vector loads is bound by L1 wavefronts -- 32 lines per instruction: 0.91 ms of smoother time at
+    //  B = 65 536, T = 200; all of it through TMA is bound by the TMA engine, see the file header.)
+    struct VecPf { float muf[R], mup1[R], al[K]; };
+    VecPf pfA, pfB;
+    auto load_vec = [&](int t, VecPf& pf) {   // means of iteration t and alpha_{t+1}
       const long bt = (long)bl * T + t;
-      float Sf[R][N], Sp1[R][N], muf[R], mup1[R], al1[K];
-      KV_UNROLL for (int r = 0; r < R; ++r) {
-        KV_UNROLL for (int j = 0; j < N; ++j) { Sf[r][j] = pf.Sf[r][j]; Sp1[r][j] = pf.Sp1[r][j]; }
-        muf[r] = pf.muf[r]; mup1[r] = pf.mup1[r];
-      }
-      KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = al_pf[k];
+      load_row<R>(a.mu_f + bt * N, pf.muf);
+      load_row<R>(a.mu_p + (bt + 1) * N, pf.mup1);
+      load_row<K>(a.alpha + (bt + 1) * K, pf.al);
+    };
+    unsigned char* ring = wsm + 2 * (int)TM::bytes;   // behind the two Sigma_s tiles; 3 x 4 KB, inside sweep 1's staging area
+    static_assert(2 * TM::bytes + 3 * 2 * TM::bytes <= (unsigned)PL::warp_bytes, "smoother ring exceeds the warp's staging area");
+    SeqBar bar_st[3] = {{tma::s32(&bars[warp][2]), 0u}, {tma::s32(&bars[warp][3]), 0u}, {tma::s32(&bars[warp][4]), 0u}};
+    auto issue_st = [&](int t, int slot) {   // elected lane
+      unsigned char* buf = ring + slot * (2 * (int)TM::bytes);
+      tma::bar_expect(bar_st[slot].addr, 2u * TM::bytes);
+      tma::load3d(tma::s32(buf), &mp.Sig_f, 0, t, b0, bar_st[slot].addr, pol_ef);
+      tma::load3d(tma::s32(buf + TM::bytes), &mp.Sig_p, 0, t + 1, b0, bar_st[slot].addr, pol_ef);
+    };
+    if (T >= 2) load_vec(T - 2, pfA);
+    if (T >= 3) load_vec(T - 3, pfB);
+    if (tma::elect_one()) {
+      if (T >= 2) issue_st(T - 2, 0);
+      if (T >= 3) issue_st(T - 3, 1);
+    }
+    int slot = 0;
+    auto smooth_iter = [&](int t, VecPf& pf) {
+      float muf[R], mup1[R], al1[K];
+      KV_UNROLL for (int r = 0; r < R; ++r) { muf[r] = pf.muf[r]; mup1[r] = pf.mup1[r]; }
+      KV_UNROLL for (int k = 0; k < K; ++k) al1[k] = pf.al[k];
       float A1[R][N];
       mix_A<C>(base, al1, 0, A1);
       if (a.a_smooth && active) {   // C_{t+1} mu_{t+1|T} (model.py:280-281): both are in hand at the top of step t
@@ -410,12 +441,20 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
         project_obs<C>(g, Ct1, mus, as);
         store_row<P>(a.a_smooth + ((long)b * T + t + 1) * P, as);
       }
-      if (t > 0) {
-        load_smooth_in<C>(a, bt - 1, 0, pf);
-        load_row<K>(a.alpha + bt * K, al_pf);
+      // requests for iteration t-2: the register set just consumed, and the ring slot iteration t+1 finished with
+      // (every lane passed the __syncwarp of that iteration after its last read of the slot)
+      if (t >= 2) {
+        load_vec(t - 2, pf);
+        if (tma::elect_one()) issue_st(t - 2, slot == 0 ? 2 : slot - 1);
       }
+      bar_st[slot].wait();
+      const float* sb = reinterpret_cast<const float*>(ring + slot * (2 * (int)TM::bytes));
+      float Sf[R][N], Sp1[R][N];
+      TM::ld_mat(sb, lane, Sf);
+      TM::ld_mat(sb + TM::floats, lane, Sp1);
       ok = smoother_step_math<C>(g, tl, Sf, Sp1, muf, mup1, A1, Sig, mus) && ok;
-      tma::wait_read0();
+      float* tSs = (t & 1) ? tSs1 : tSs0;      // (T is even: step T-1 used tSs1, step T-2 uses tSs0, ...)
+      if (KV_SEQ_OUT_BUFS == 2) tma::wait_read1(); else tma::wait_read0();
       __syncwarp();
       TM::st_mat(tSs, lane, Sig);
       if (active) store_row<N>(a.mu_s + ((long)b * T + t) * N, mus);
@@ -425,6 +464,12 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 3) k_seq_fwd(Args a, Bas
         tma::store3d(&mp.Sig_s, 0, t, b0, tma::s32(tSs), pol_ef);
         tma::commit();
       }
+      slot = (slot == 2) ? 0 : slot + 1;
+    };
+#pragma unroll 1
+    for (int t = T - 2; t >= 0; t -= 2) {
+      smooth_iter(t, pfA);
+      if (t >= 1) smooth_iter(t - 1, pfB);
     }
     if (a.a_smooth && active) {   // t = 0
       float al0[K], Ct0[R][P], as[P];

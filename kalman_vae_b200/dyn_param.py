@@ -150,9 +150,14 @@ class MarkovVariationalRegimePosterior(nn.Module):
 class SwitchingDynamicsParameter(nn.Module):
     """Mirror of kvae/kalman/switch_dyn_param.py:7-95 (SKVAE regime posterior)."""
 
-    def __init__(self, A, B, C, Q=None, prior=None, hidden_lstm=32, markov_regime_posterior=None):
+    def __init__(self, A, B, C, Q=None, prior=None, hidden_lstm=32, markov_regime_posterior=None, reference_rng=False):
         super().__init__()
         self.is_switching_dynamics = True
+        # reference_rng=True: draw the Gumbel noise as the reference does -- one [B,K] exponential draw per time step
+        # (torch.nn.functional.gumbel_softmax called T times, switch_dyn_param.py:52,69) -- so that a run seeded like a
+        # reference run samples the SAME regimes; the default draws the whole [B,T,K] chain in one call (one launch
+        # instead of T, a different stream of the same distribution)
+        self.reference_rng = bool(reference_rng)
         self.K = A.size(0)
         self.n, self.m, self.p = A.size(1), B.size(2), C.size(1)
         self.tau = 0.5
@@ -198,6 +203,10 @@ class SwitchingDynamicsParameter(nn.Module):
     def _draw_gumbel(self, batch, T, K, like):
         """Gumbel(0,1) noise for every step: the draw torch.nn.functional.gumbel_softmax makes per call
         (`-empty_like(logits).exponential_().log()`), here for the whole [B,T,K] chain at once."""
+        if self.reference_rng:
+            # gumbel_softmax's own draw, per step and in the reference's order: -empty_like(logits_t).exponential_().log()
+            return torch.stack([-torch.empty(batch, K, dtype=like.dtype, device=like.device).exponential_().log()
+                                for _ in range(T)], dim=1)
         return -torch.empty(batch, T, K, dtype=like.dtype, device=like.device).exponential_().log()
 
     def compute_batch(self, a_seq, is_training=True):

@@ -87,3 +87,25 @@ def test_switching_kvae_trains_with_the_drop_in():
     losses = [float(new.step(x)) for _ in range(8)]
     assert all(l == l and abs(l) < 1e9 for l in losses), losses
     assert min(losses[4:]) < losses[0], losses
+
+
+def test_switching_reference_rng_samples_the_same_regimes():
+    """SwitchingDynamicsParameter(reference_rng=True): the Gumbel noise is drawn per step in the reference's order
+    (switch_dyn_param.py:52,69), so a drop-in run seeded like a reference-on-CUDA run picks IDENTICAL regimes (eval mode:
+    hard one-hot samples) and the same smoothed states."""
+    ref, new = _pair("switching")
+    new.model.kalman_filter.dyn_params.reference_rng = True
+    x = ref.synthetic_batch(seed=9).cuda()
+    outs = {}
+    for name, st in (("ref", ref), ("new", new)):
+        m = st.model
+        m.eval()
+        with torch.no_grad():
+            torch.manual_seed(4321)
+            m.kalman_filter.dyn_params.reset_state()
+            outs[name] = m(x, mask=torch.ones(32, 20, device=x.device))
+    yr, yn = outs["ref"]["state_probs"], outs["new"]["state_probs"]
+    assert torch.equal(yr.argmax(-1), yn.argmax(-1))                      # identical regime picks
+    assert float((yr - yn).abs().max()) < 1e-5
+    assert rel(outs["new"]["mus_smooth"], outs["ref"]["mus_smooth"]) < 5e-5
+    assert rel(outs["new"]["Sigmas_smooth"], outs["ref"]["Sigmas_smooth"]) < 5e-5

@@ -12,7 +12,7 @@ for line in out.splitlines():
         fn = re.sub(r"\(.*", "", fn)
         hist[fn] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m and fn:
         hist[fn][m.group(1)] += 1
 for fn, h in hist.items():
