@@ -52,37 +52,72 @@ def _run(cmd, log):
     return p.stdout
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
+def _compile(shape_list, obj_dir, lib_path, override_list, verbose=False):
+    os.makedirs(obj_dir, exist_ok=True)
     jobs = []
-    for (n, p, m, k) in shapes():
-        o = os.path.join(OBJ, f"shape_{n}_{p}_{m}_{k}.o")
+    for (n, p, m, k) in shape_list:
+        o = os.path.join(obj_dir, f"shape_{n}_{p}_{m}_{k}.o")
         cmd = [NVCC, *ARCH, *FLAGS, f"-DKV_N={n}", f"-DKV_P={p}", f"-DKV_M={m}", f"-DKV_K={k}",
                "-c", os.path.join(CSRC, "kvae_shape.cu"), "-o", o]
         jobs.append((cmd, o))
-    o = os.path.join(OBJ, "capi.o")
+    o = os.path.join(obj_dir, "capi.o")
     extra = []
-    if os.environ.get("KVAE_SHAPES"):
-        hdr = os.path.join(OBJ, "shape_list_override.h")
+    if override_list:
+        hdr = os.path.join(obj_dir, "shape_list_override.h")
         with open(hdr, "w") as f:
-            f.write("#define KVAE_FOR_EACH_SHAPE(X) " + " ".join(f"X({n},{p},{m},{k})" for (n, p, m, k) in shapes()) + "\n")
+            f.write("#define KVAE_FOR_EACH_SHAPE(X) " + " ".join(f"X({n},{p},{m},{k})" for (n, p, m, k) in shape_list) + "\n")
         extra = ["--pre-include", hdr]
     jobs.append(([NVCC, *ARCH, *FLAGS, *extra, "-c", os.path.join(CSRC, "kvae_capi.cu"), "-o", o], o))
-    o = os.path.join(OBJ, "regime.o")
-    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_regime.cu"), "-o", o], o))
-    o = os.path.join(OBJ, "dp.o")
-    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_dp.cu"), "-o", o], o))
-    o = os.path.join(OBJ, "vae.o")
-    jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "kvae_vae.cu"), "-o", o], o))
+    for name in ("regime", "dp", "vae"):
+        o = os.path.join(obj_dir, name + ".o")
+        jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, f"kvae_{name}.cu"), "-o", o], o))
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
     if verbose:
         for out in outs:
             sys.stdout.write(out)
-    _run([NVCC, *ARCH, "-shared", "-o", LIB, *[j[1] for j in jobs]], os.path.join(OBJ, "link.log"))
-    return LIB
+    tmp = lib_path + f".tmp{os.getpid()}"
+    _run([NVCC, *ARCH, "-shared", "-o", tmp, *[j[1] for j in jobs]], os.path.join(obj_dir, "link.log"))
+    os.replace(tmp, lib_path)   # atomic: a concurrent loader never sees a half-written library
+    return lib_path
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    return _compile(shapes(), OBJ, LIB, bool(os.environ.get("KVAE_SHAPES")), verbose)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Shapes on demand.  KVAEConfig (kvae/utils/config.py:4-60) allows any (a_dim, z_dim, u_dim, num_modes); the default
+# library instantiates the five tuples of kvae_configs.h.  For any other tuple capi.lib_for() calls build_shape_lib(),
+# which compiles the SAME sources for that one tuple into kalman_vae_b200/_jit/ (nvcc is part of the image; ~0.5-2 min,
+# once -- the library is cached on disk and re-used while the sources are unchanged).
+# ---------------------------------------------------------------------------------------------------------
+JIT_DIR = os.path.join(HERE, "_jit")
+
+
+def shape_lib_path(n, p, m, k):
+    return os.path.join(JIT_DIR, f"libkvae_kalman_{n}_{p}_{m}_{k}.so")
+
+
+def build_shape_lib(n, p, m, k, force=False, verbose=False):
+    lib = shape_lib_path(n, p, m, k)
+    if not force and os.path.exists(lib) and all(os.path.getmtime(s) <= os.path.getmtime(lib) for s in _sources()):
+        return lib
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"shape (n={n}, p={p}, m={m}, K={k}) is not in libkvae_kalman.so and {NVCC} is not available to build it")
+    os.makedirs(JIT_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(JIT_DIR, f".lock_{n}_{p}_{m}_{k}"), "w") as lk:   # ranks of one job build it once
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in _sources()):
+                sys.stderr.write(f"[kalman_vae_b200] compiling the kernels for shape (n={n}, p={p}, m={m}, K={k}) -> {lib}\n")
+                _compile([(n, p, m, k)], os.path.join(JIT_DIR, f"_obj_{n}_{p}_{m}_{k}"), lib, True, verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+    return lib
 
 
 if __name__ == "__main__":

@@ -61,16 +61,9 @@ class KvaeError(RuntimeError):
 _lib = None
 
 
-def lib():
-    """Loads the native library (raises if it has not been built: there is no CPU path)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise KvaeError(
-            f"{LIB_PATH} not found: build it with `python -m kalman_vae_b200.build` "
-            "(or __graft_entry__.build()). The Kalman hot path has no CPU fallback.")
-    L = ctypes.CDLL(LIB_PATH)
+def _load(path):
+    """dlopen + ctypes signatures of one build of the library (the default one or a shape built on demand)."""
+    L = ctypes.CDLL(path)
     L.kvae_abi_version.restype = c_int
     L.kvae_last_error.restype = c_char_p
     L.kvae_supported.argtypes = [POINTER(KvaeDims)]
@@ -108,8 +101,40 @@ def lib():
     L.kvae_kf_mask_partials_count.argtypes = [POINTER(KvaeDims)]
     L.kvae_kf_mask_partials_count.restype = c_size_t
     if L.kvae_abi_version() != 6:
-        raise KvaeError("libkvae_kalman.so ABI version mismatch")
-    _lib = L
+        raise KvaeError(f"{path}: ABI version mismatch")
+    return L
+
+
+def lib():
+    """Loads the native library (raises if it has not been built: there is no CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KvaeError(
+            f"{LIB_PATH} not found: build it with `python -m kalman_vae_b200.build` "
+            "(or __graft_entry__.build()). The Kalman hot path has no CPU fallback.")
+    _lib = _load(LIB_PATH)
+    return _lib
+
+
+# Shapes on demand: (n, p, m, K) tuples outside kvae_configs.h get their own build of the same sources
+# (kalman_vae_b200/build.py build_shape_lib; KVAE_JIT=0 switches this off and such shapes raise).
+_shape_libs = {}
+
+
+def lib_for(dims):
+    """The library build that instantiates dims' (n, p, m, K): the default one, or one compiled on demand."""
+    key = (dims.n, dims.p, dims.m, dims.K)
+    L = _shape_libs.get(key)
+    if L is not None:
+        return L
+    L = lib()
+    probe = KvaeDims(1, 1, dims.n, dims.p, dims.m, dims.K, 0, 0, 0, 0)
+    if not L.kvae_supported(byref(probe)) and os.environ.get("KVAE_JIT", "1") != "0" and min(key) >= 1 and dims.n <= 16:
+        from . import build as kbuild
+        L = _load(kbuild.build_shape_lib(*key))
+    _shape_libs[key] = L
     return L
 
 
@@ -142,9 +167,9 @@ def _ptr(t, name, device=None):
     return p
 
 
-def _check(rc, what):
+def _check(rc, what, L=None):
     if rc != 0:
-        raise KvaeError(f"{what} failed (status {rc}): {lib().kvae_last_error().decode()}")
+        raise KvaeError(f"{what} failed (status {rc}): {(L or lib()).kvae_last_error().decode()}")
 
 
 FLAG_SMOOTH_ONLY = 1
@@ -158,11 +183,11 @@ def make_dims(B, T, n, p, m, K, q_per_mode, c_shared, lanes=0, flags=0):
 
 
 def supported(dims) -> bool:
-    return bool(lib().kvae_supported(byref(dims)))
+    return bool(lib_for(dims).kvae_supported(byref(dims)))
 
 
 def pick_lanes(dims) -> int:
-    return int(lib().kvae_pick_lanes(byref(dims)))
+    return int(lib_for(dims).kvae_pick_lanes(byref(dims)))
 
 
 def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Sigma_init=None,
@@ -175,7 +200,7 @@ def make_inputs(Y, U, mask, alpha, A, Bm, C, Q, R, mu0, Sigma0, mu_init=None, Si
 
 
 def mask_partials_count(dims) -> int:
-    return int(lib().kvae_kf_mask_partials_count(byref(dims)))
+    return int(lib_for(dims).kvae_kf_mask_partials_count(byref(dims)))
 
 
 def make_states(mus_filt, Sigmas_filt, mus_pred, Sigmas_pred, mus_smooth=None, Sigmas_smooth=None, mask_partials=None,
@@ -196,24 +221,24 @@ def _stream(device):
 
 
 def filter_smooth_fwd(dims, inputs, states, A_list, B_list, C_list, info, device):
-    rc = lib().kvae_kf_filter_smooth_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"),
+    rc = lib_for(dims).kvae_kf_filter_smooth_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"),
                                          _ptr(B_list, "B_list"), _ptr(C_list, "C_list"), _ptr(info, "info"),
                                          device.index, _stream(device))
-    _check(rc, "kvae_kf_filter_smooth_fwd")
+    _check(rc, "kvae_kf_filter_smooth_fwd", lib_for(dims))
 
 
 def filter_lstm_fwd(dims, inputs, states, A_list, B_list, C_list, lstm_tensors, hidden, alpha_out, info, device):
     """Filter sweep with the LSTM dynamics network in the loop.  lstm_tensors: dict with w_ih, w_hh, b_ih, b_hh, w_head,
     b_head (+ optional h0, c0, h_out, c_out)."""
     ls = KvaeLstm(*[_ptr(lstm_tensors.get(k), "lstm." + k) for k, _ in KvaeLstm._fields_[:-1]], int(hidden))
-    rc = lib().kvae_kf_filter_lstm_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"), _ptr(B_list, "B_list"),
+    rc = lib_for(dims).kvae_kf_filter_lstm_fwd(byref(dims), byref(inputs), byref(states), _ptr(A_list, "A_list"), _ptr(B_list, "B_list"),
                                        _ptr(C_list, "C_list"), byref(ls), _ptr(alpha_out, "alpha_out"), _ptr(info, "info"),
                                        device.index, _stream(device))
-    _check(rc, "kvae_kf_filter_lstm_fwd")
+    _check(rc, "kvae_kf_filter_lstm_fwd", lib_for(dims))
 
 
 def elbo_workspace_bytes(dims) -> int:
-    return int(lib().kvae_kf_elbo_workspace_bytes(byref(dims)))
+    return int(lib_for(dims).kvae_kf_elbo_workspace_bytes(byref(dims)))
 
 
 def _jit(jitter):
@@ -227,26 +252,26 @@ def _jit(jitter):
 
 def elbo_fwd(dims, inputs, states, eps, jitter, terms, workspace, info, device):
     js, opts = _jit(jitter)
-    rc = lib().kvae_kf_elbo_fwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
+    rc = lib_for(dims).kvae_kf_elbo_fwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
                                    byref(opts) if opts is not None else None,
                                    _ptr(terms, "terms"), c_void_p(workspace.data_ptr()), _ptr(info, "info"),
                                    device.index, _stream(device))
-    _check(rc, "kvae_kf_elbo_fwd")
+    _check(rc, "kvae_kf_elbo_fwd", lib_for(dims))
 
 
 def bwd_workspace_bytes(dims) -> int:
-    return int(lib().kvae_kf_bwd_workspace_bytes(byref(dims)))
+    return int(lib_for(dims).kvae_kf_bwd_workspace_bytes(byref(dims)))
 
 
 def bwd(dims, inputs, states, eps, jitter, g_elbo, terms, cot, grads, workspace, info, device):
     cot_s = KvaeCotangents(*[_ptr(cot.get(k) if cot else None, "cot." + k) for k, _ in KvaeCotangents._fields_])
     grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
     js, opts = _jit(jitter)
-    rc = lib().kvae_kf_bwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
+    rc = lib_for(dims).kvae_kf_bwd_ex(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(js),
                               byref(opts) if opts is not None else None,
                               _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(cot_s), byref(grads_s),
                               c_void_p(workspace.data_ptr()), _ptr(info, "info"), device.index, _stream(device))
-    _check(rc, "kvae_kf_bwd")
+    _check(rc, "kvae_kf_bwd", lib_for(dims))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -279,10 +304,10 @@ def dp_destroy(comm):
 def bwd_dp(dims, inputs, states, eps, jitter, g_elbo, terms, grads, workspace, info, device, comm):
     """kvae_kf_bwd + the cross-rank exchange in its final kernel (dims.flags must hold WITH_ELBO | RAW_SUMS)."""
     grads_s = KvaeGrads(*[_ptr(grads.get(k), k) for k, _ in KvaeGrads._fields_])
-    rc = lib().kvae_kf_bwd_dp(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
+    rc = lib_for(dims).kvae_kf_bwd_dp(byref(dims), byref(inputs), byref(states), _ptr(eps, "eps"), c_float(jitter),
                               _ptr(g_elbo, "g_elbo"), _ptr(terms, "terms"), byref(grads_s), c_void_p(workspace.data_ptr()),
                               _ptr(info, "info"), device.index, _stream(device), comm)
-    _check(rc, "kvae_kf_bwd_dp")
+    _check(rc, "kvae_kf_bwd_dp", lib_for(dims))
 
 
 def dp_finalize(dims, comm, grads, terms, info, device):

@@ -27,6 +27,8 @@ bool variant_ok(const kvae_dims& d) { return (d.q_per_mode != 0) == (d.c_shared 
 //  * n = 16: L = 16 (fewer spills).  n = 8: smallest count that still gives >= 8 warps per SM.
 int pick_lanes(const kvae_dims& d) {
   const int n = d.n;
+  if (n > 0 && (n & (n - 1)) != 0)   // z_dim not a power of two: its largest power-of-two divisor (see kvae_shape.cu)
+    return (n % 16 == 0) ? 16 : (n % 8 == 0) ? 8 : (n % 4 == 0) ? 4 : (n % 2 == 0) ? 2 : 1;
   if (n == 4 && d.m == 4 && d.T % 4 == 0 && d.B >= 32768 && !(d.flags & KVAE_FLAG_SMOOTH_ONLY)) return 1;
   if (n <= 4) return n < 1 ? 1 : n;
   if (n != 8) return n;

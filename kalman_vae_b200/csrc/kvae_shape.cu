@@ -8,8 +8,15 @@ namespace kvae {
 namespace {
 constexpr int N = KV_N, P = KV_P, M = KV_M, K = KV_K;
 
-// lane counts instantiated for this z_dim (rows per lane R = N / L kept <= 4 for N >= 8)
-#if KV_N <= 4
+// lane counts instantiated for this z_dim (rows per lane R = N / L kept <= 4 for N >= 8).  A lane count must be a power
+// of two that divides z_dim: a z_dim that is not a power of two (shapes built on demand, kalman_vae_b200/build.py
+// build_shape_lib) runs on its largest power-of-two divisor (z_dim odd: one lane per sequence).
+#define KV_N_POW2 ((KV_N & (KV_N - 1)) == 0)
+#if !KV_N_POW2
+#define KV_G ((KV_N % 16 == 0) ? 16 : (KV_N % 8 == 0) ? 8 : (KV_N % 4 == 0) ? 4 : (KV_N % 2 == 0) ? 2 : 1)
+#define KV_FOR_EACH_L(X) X(KV_G)
+#define KV_L_OK(l) ((l) == KV_G)
+#elif KV_N <= 4
 #define KV_FOR_EACH_L(X) X(1) X(2) X(KV_N)
 #define KV_L_OK(l) ((l) == 1 || (l) == 2 || (l) == KV_N)
 #elif KV_N == 8
@@ -85,7 +92,7 @@ int ShapeOps<N, P, M, K>::fwd(const kvae_dims& d, const kvae_inputs& in, const k
 template <>
 int ShapeOps<N, P, M, K>::fwd_lstm(const kvae_dims& d, const kvae_inputs& in, const kvae_states& st, float* A_list, float* B_list,
                                    float* C_list, const kvae_lstm& lw, float* alpha_out, int32_t* info, cudaStream_t s) {
-#if KV_K > 1 && KV_N <= 8
+#if KV_K > 1 && KV_N <= 8 && KV_N_POW2
   constexpr int LW = N;   // one row per lane
   if (d.lanes != LW || d.q_per_mode || lw.hidden > 52 || lw.hidden < 1) return -3;
   Args a = make_args(d, in, st, info);

@@ -80,7 +80,8 @@ class Problem:
         if not ok:
             raise capi.KvaeError(
                 f"shape (n={n}, p={p}, m={m}, K={K}, switching={self.q_per_mode}, lanes={self.lanes}) is not "
-                "instantiated in libkvae_kalman.so; add it to kalman_vae_b200/csrc/kvae_configs.h and rebuild")
+                "instantiated (libkvae_kalman.so holds the tuples of kalman_vae_b200/csrc/kvae_configs.h; any other (n <= 16, p, m, "
+                "K) is compiled on demand unless KVAE_JIT=0; lanes must be a power of two dividing n)")
 
     @property
     def shape(self):

@@ -260,7 +260,7 @@ class KalmanFilter(nn.Module):
         n, m, K = self.n, self.m, dyn.A.size(0)
         if not (isinstance(lstm, nn.LSTM) and isinstance(head, nn.Linear) and lstm.num_layers == 1 and not lstm.bidirectional
                 and lstm.bias and getattr(lstm, "proj_size", 0) == 0 and lstm.input_size == p and lstm.hidden_size <= 52
-                and head.bias is not None and n <= 8 and K > 1 and self.lanes in (0, n)):
+                and head.bias is not None and n <= 8 and (n & (n - 1)) == 0 and K > 1 and self.lanes in (0, n)):
             return None
         dev = Y.device
         H = lstm.hidden_size

@@ -35,7 +35,8 @@ def test_abi_version_and_support_table(lib):
     assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 1   # >= 32768 sequences, T % 4 == 0: thread per sequence
     assert capi.pick_lanes(capi.make_dims(65536, 1001, 4, 2, 4, 3, False, False, 0)) == 4   # T % 4 != 0: lane groups
     assert capi.supported(capi.make_dims(8, 20, 16, 8, 16, 8, True, True, 16))
-    assert not capi.supported(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0))     # shape not instantiated
+    raw = lambda d: bool(L.kvae_supported(ctypes.byref(d)))
+    assert not raw(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0))   # not in the default library (capi.supported would build it on demand)
     assert not capi.supported(capi.make_dims(8, 20, 4, 2, 4, 3, True, False, 0))      # mixed variant
     assert not capi.supported(capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 3))     # lanes must divide n
 
@@ -69,4 +70,19 @@ def test_data_parallel_and_regime_entries_reject_bad_arguments(lib):
     assert L.kvae_kf_mask_partials_count(None) == 0
     d = capi.make_dims(8192, 20, 4, 2, 4, 3, False, False, 0)
     assert capi.mask_partials_count(d) == 8192 // (128 // 4)                # one partial per forward CTA (128 threads, L = 4)
-    assert capi.mask_partials_count(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0)) == 0   # shape not instantiated
+    assert L.kvae_kf_mask_partials_count(ctypes.byref(capi.make_dims(8, 20, 5, 2, 4, 3, False, False, 0))) == 0   # shape not in the default library
+
+
+def test_shape_on_demand_is_built_and_loaded(lib):
+    """A (n, p, m, K) tuple outside kvae_configs.h: capi.lib_for compiles the same sources for it (nvcc, cached under
+    kalman_vae_b200/_jit/) and the resulting library exports the whole ABI; KVAE_JIT=0 keeps the old behaviour."""
+    d = capi.make_dims(8, 20, 3, 2, 3, 2, False, False, 0)
+    assert not capi.lib().kvae_supported(ctypes.byref(d))
+    L = capi.lib_for(d)
+    assert L is not capi.lib()
+    assert capi.supported(d) and capi.supported(capi.make_dims(8, 20, 3, 2, 3, 2, True, True, 0))
+    assert capi.pick_lanes(d) == 1                                            # odd z_dim: one lane per sequence
+    assert not capi.supported(capi.make_dims(8, 20, 3, 2, 3, 2, False, False, 2))
+    assert capi.mask_partials_count(d) > 0 and capi.bwd_workspace_bytes(d) > 0
+    for s in capi.EXPORTED_SYMBOLS:
+        assert hasattr(L, s), s

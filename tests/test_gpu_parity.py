@@ -207,3 +207,44 @@ def test_projections_emitted_by_the_sweeps(name):
         st, *_ = F.smooth_fwd(pb, smooth=True, lists=False, projections=True)
         for k in ("a_filt", "a_smooth"):
             check_close(f"{name}.L{lanes}.{k}", getattr(st, k), want32[k], want[k], rtol=2e-5)
+
+
+# shapes outside kvae_configs.h: built on demand from the same sources (kalman_vae_b200/build.py build_shape_lib;
+# __graft_entry__.build() pre-builds exactly these so that the GPU box only loads them)
+ON_DEMAND_SHAPES = [(3, 2, 3, 2), (6, 3, 5, 2)]
+
+
+@pytest.mark.parametrize("dims", ON_DEMAND_SHAPES)
+@pytest.mark.parametrize("switching", [False, True])
+def test_shape_built_on_demand_matches_oracle(dims, switching):
+    """KVAEConfig allows any (a_dim, z_dim, u_dim, num_modes) (kvae/utils/config.py:4-60).  A tuple that the default
+    library does not instantiate -- here z_dim = 3 (odd: one lane per sequence) and z_dim = 6 (two lanes) -- gets its own
+    build of the same kernels; forward outputs, ELBO and training gradients against the CPU oracle in fp32 / fp64."""
+    from kalman_vae_b200 import capi
+    from kalman_vae_b200.synthetic import Shape, make_case
+    from oracle import kalman_oracle as ko
+    n, p, m, K = dims
+    dev = torch.device("cuda:0")
+    assert not capi.lib().kvae_supported(capi.make_dims(1, 1, n, p, m, K, switching, switching)), "shape is in the default library"
+    case = make_case(Shape(70, 11, n, p, m, K, switching, switching), seed=5, mask_kind="bernoulli", zero_u=False, c_std=0.3)
+    r32 = ko.run_case(case, torch.float32, want_grads=True)
+    r64 = ko.run_case(case, torch.float64, want_grads=True)
+    pb, g = problem(case, 0, dev)
+    assert capi.lib_for(pb.dims) is not capi.lib()
+    F.info_word(dev).zero_()
+    st, A_list, B_list, C_list = F.smooth_fwd(pb)
+    got = dict(mus_smooth=st.mus_smooth, Sigmas_smooth=st.Sigmas_smooth, mus_filt=st.mus_filt, Sigmas_filt=st.Sigmas_filt,
+               mus_pred=st.mus_pred, Sigmas_pred=st.Sigmas_pred, A_list=A_list, B_list=B_list, C_list=C_list)
+    for k in OUT_NAMES:
+        check_close(f"{dims}.{k}", got[k], r32[k], r64[k])
+    t_f = torch.empty(8, device=dev)
+    pb.mask_partials = st.mask_partials
+    gr = F.adjoint(pb, st, eps=g["eps"], g_elbo=torch.ones(1, device=dev), terms=t_f, with_elbo=True)
+    torch.cuda.synchronize()
+    assert int(F.info_word(dev)) == 0
+    check_close(f"{dims}.elbo", t_f[5], r32["elbo"], r64["elbo"])
+    gr = dict(dY=gr["dY"], dU=gr["dU"], dalpha=gr["dalpha"], dA=gr["dA"], dB=gr["dBm"], dC=gr["dC"], dQ=gr["dQ"])
+    for k, v in gr.items():
+        if v is not None and k in r64 and float(r64[k].abs().max()) > 0:
+            e32, e64, floor = check_close(f"{dims}.{k}", v, r32[k], r64[k])
+            print(f"{dims} switching={switching} {k}: e32 {e32:.1e} e64 {e64:.1e} floor {floor:.1e}")
