@@ -742,23 +742,35 @@ def run_kvae(cx: Ctx):
     res = {}
     if rank == 0:
         cx.sampler.start()
-    for label, drop_in in (("drop_in", True), ("reference_ops", False)):
-        stepper = kvae_step.ReferenceTrainStep(device=dev, drop_in=drop_in, seed=10 + rank, distributed=world > 1)
+    for label, drop_in in (("drop_in_graphed", True), ("drop_in", True), ("reference_ops", False)):
+        graphed = label == "drop_in_graphed"
+        if graphed:   # the whole step captured in CUDA graphs (kvae_step.GraphedTrainStep)
+            stepper = kvae_step.GraphedTrainStep(device=dev, seed=10 + rank, distributed=world > 1)
+        else:
+            stepper = kvae_step.ReferenceTrainStep(device=dev, drop_in=drop_in, seed=10 + rank, distributed=world > 1)
         xs_host = [stepper.synthetic_batch(seed=100 * rank + i).pin_memory() for i in range(4)]
-        run = lambda i: stepper.step(xs_host[i % 4].to(dev, non_blocking=True))
+        if graphed:
+            stepper.capture(xs_host[0])
+            out_host = torch.zeros(1).pin_memory()
+
+            def run(i):   # per step: H2D of the frames into the static buffer, replay, D2H of the loss
+                loss = stepper.step(xs_host[i % 4])
+                out_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        else:
+            run = lambda i: stepper.step(xs_host[i % 4].to(dev, non_blocking=True))
         n = steps if drop_in else max(3, min(steps, 10))
         for i in range(max(3, min(args.warmup, 5))):
             run(i)
         blocks = cx.timed_blocks(run, n, blocks=3 if drop_in else 1)
         res[label] = {"ms_per_step": statistics.median(blocks), "ms_per_step_blocks": blocks, "steps_per_block": n,
-                      "loss_last": float(stepper.last_loss)}
+                      "loss_last": float(stepper.last_loss.detach())}
         B, T = stepper.batch, stepper.T
         h2d = xs_host[0].numel() * 4
         del stepper
         torch.cuda.empty_cache()
     clocks = cx.sampler.stop() if rank == 0 else None
     if rank == 0:
-        ms = res["drop_in"]["ms_per_step_blocks"][0]
+        ms = res["drop_in_graphed"]["ms_per_step_blocks"][0]
         value = world * B * T / (ms * 1e-3)
         emit({
             "metric": METRICS["cfg5"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -766,13 +778,17 @@ def run_kvae(cx: Ctx):
             "config": {"workload": workload_text("cfg5"),
                        "what": "reference KVAE module (conv encoder / decoder in PyTorch) with kalman_vae_b200.KalmanFilter and "
                                "DynamicsParameter swapped in; per step: H2D of the frames, forward, compute_loss, backward, NCCL "
-                               "all-reduce of all gradients (N > 1), clip_grad_norm_(10), Adam(lr 0.007)",
+                               "all-reduce of all gradients (N > 1), clip_grad_norm_(10), Adam(lr 0.007).  value = the step captured "
+                               "in CUDA graphs (kvae_step.GraphedTrainStep: forward + loss + backward [+ eager NCCL all-reduce] + "
+                               "clip + Adam replayed; compute_loss's two diagnostic host reads left out); kvae_step.drop_in = the "
+                               "same step eager, kvae_step.reference_ops = eager with the reference's own Kalman ops",
                        "collective": "nccl all-reduce of the flattened gradients" if world > 1 else "none"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms,
                     "api": "the training-step body of kvae/train/train.py:32-58 on the reference KVAE with the drop-in Kalman block; "
                            "the batch of frames comes from pinned host memory every step and the loss is read back"},
             "kvae_step": res,
-            "speedup_over_reference_ops_same_gpu": res["reference_ops"]["ms_per_step"] / res["drop_in"]["ms_per_step"],
+            "speedup_over_reference_ops_same_gpu": res["reference_ops"]["ms_per_step"] / res["drop_in_graphed"]["ms_per_step"],
+            "speedup_over_reference_ops_same_gpu_eager": res["reference_ops"]["ms_per_step"] / res["drop_in"]["ms_per_step"],
             "gpu_launches": None, "roofline": None, "cpu_baseline": None, "clocks": clocks,
         })
 

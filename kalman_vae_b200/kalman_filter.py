@@ -78,7 +78,10 @@ class KalmanFilter(nn.Module):
 
     # ------------------------------------------------------------------ deferred device-side checks
     def _defer(self, flag, kind):
-        """Queues a device int32 `flag` (non-zero = failure) for a look at the start of the next public call."""
+        """Queues a device int32 `flag` (non-zero = failure) for a look at the start of the next public call.
+        (Not while a CUDA graph is being captured: a replay runs no host code, so there is nobody to look.)"""
+        if torch.cuda.is_current_stream_capturing():
+            return
         if self._ring is None:     # pinned words are allocated ONCE (cudaHostAlloc synchronises the device)
             self._ring = torch.zeros(16, dtype=torch.int32).pin_memory()
             self._ring_i = 0
@@ -92,6 +95,8 @@ class KalmanFilter(nn.Module):
         self._deferred.append((ev, host, kind))
 
     def _poll_deferred(self, block_oldest=False):
+        if not self._deferred or torch.cuda.is_current_stream_capturing():
+            return
         keep = []
         for i, (ev, host, kind) in enumerate(self._deferred):
             if block_oldest and i == 0:

@@ -143,3 +143,110 @@ class ReferenceTrainStep:
         self.last = losses
         self.last_loss = loss.detach()
         return self.last_loss
+
+
+class GraphedTrainStep(ReferenceTrainStep):
+    """The same optimisation step captured ONCE into CUDA graphs and replayed: at batch 32 the eager step is bound by
+    Python / launch overhead (~300 small kernels and three host reads per step), not by the GPU.
+
+    What is captured: the reference model's `forward` as it is (encoder, this package's Kalman block, decoder), the loss
+    composition of `KVAE.compute_loss` (model.py:189-229: vae_loss + kalman_filter.elbo; its two diagnostic host reads
+    `count_active_units(...)` / `.item()` at :231-240 cannot be part of a graph and are left out), backward, gradient
+    clipping and Adam (capturable=True: the same update with its step counter on the device).  The VAE-side reductions
+    run in this package's kernels (kalman_vae_b200.vae_loss): the reference's vae_loss builds
+    device constants from host scalars on every call (losses.py:17), which a capture cannot contain.
+    Data parallel: graph 1 = forward + backward, then ONE eager NCCL all-reduce of the flattened gradients, graph 2 =
+    clip + Adam.  Per step the host copies the batch into the static input buffer and replays.
+    """
+
+    def __init__(self, device, dynamics_model="lstm", batch=32, T=20, seed=10, distributed=False, lr=0.007,
+                 grad_clip_norm=10.0):
+        super().__init__(device, True, dynamics_model, batch, T, seed, distributed, lr, grad_clip_norm)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, capturable=True)
+        self.model.kalman_filter.check_info = False      # no host reads inside a graph; call check() when convenient
+        self.g_main = self.g_opt = None
+        self.static_x = torch.zeros(batch, T, 1, 32, 32, device=device)
+        self.mask = torch.ones(batch, T, device=device)                  # train.py:41
+        self.static_loss = None
+        self._flat = None
+
+    def _loss(self):
+        model, cfg = self.model, self.model.config
+        x, mask = self.static_x, self.mask
+        model.kalman_filter.dyn_params.reset_state()                     # train.py:34
+        out = model(x, mask=mask)                                        # train.py:45
+        from .vae_loss import vae_loss
+        x_var = cfg.noise_pixel_var
+        vae_elbo, _, _ = vae_loss(x, out.get("x_logits", out["x_recon"]), x_var, out["a_samples"], out["a_mu"], out["a_var"],
+                                  scale_reconstruction=cfg.scale_reconstruction, mask=mask, out_distr=cfg.out_distr,
+                                  beta=model.beta)                       # model.py:208-215
+        A_list, B_list, C_list = out["ABC"]
+        elbo_kf = model.kalman_filter.elbo(out["mus_smooth"], out["Sigmas_smooth"], out["a_samples"], out["u"],
+                                           A_list, B_list, C_list, mask=mask)   # model.py:218-222
+        return -(vae_elbo + elbo_kf)                                     # model.py:225-226 with both weights 1
+
+    def _allreduce(self):
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        if self._flat is None:
+            self._flat = torch.empty(sum(g.numel() for g in grads), device=self.device)
+        torch._foreach_copy_(list(self._flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        torch.distributed.all_reduce(self._flat, op=torch.distributed.ReduceOp.SUM)
+        self._flat /= torch.distributed.get_world_size()
+        torch._foreach_copy_([g.reshape(-1) for g in grads], list(self._flat.split([g.numel() for g in grads])))
+
+    def _update(self):
+        if self.clip and self.clip > 0:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)   # train.py:55-56
+        self.opt.step()                                                          # train.py:58
+
+    def capture(self, x_example, warmup=3):
+        dev = self.device
+        self.static_x.copy_(x_example.to(dev).float())
+        kf = self.model.kalman_filter
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):            # eager warm-up on a side stream (allocator, cuDNN plans, lazy inits)
+            for _ in range(warmup):
+                self.opt.zero_grad(set_to_none=True)
+                self._loss().backward()
+                if self.distributed:
+                    self._allreduce()
+                self._update()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        kf._poll_deferred()
+        kf._deferred = []
+        self.opt.zero_grad(set_to_none=True)
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            self.static_loss = self._loss()
+            self.static_loss.backward()
+            if not self.distributed:
+                self._update()
+        if self.distributed:
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_main.pool()):
+                self._update()
+        return self
+
+    def step(self, x):
+        if self.g_main is None:
+            self.capture(x)
+        self.static_x.copy_(x, non_blocking=True)
+        self.g_main.replay()
+        if self.distributed:
+            self._allreduce()
+            self.g_opt.replay()
+        self.last_loss = self.static_loss
+        return self.static_loss
+
+    def check(self):
+        """One synchronising look at the Kalman kernels' status word (a replayed graph runs no host code, so the lazy
+        checks of KalmanFilter.elbo are off): raises if a factorisation met a non-positive pivot since the last call."""
+        from .functional import info_word
+        w = info_word(self.device)
+        code = int(w.item())
+        if code:
+            w.zero_()
+            raise torch.linalg.LinAlgError(f"kvae: a Cholesky / LU pivot was not positive in a replayed step (status word {code})")

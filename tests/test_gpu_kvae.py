@@ -109,3 +109,30 @@ def test_switching_reference_rng_samples_the_same_regimes():
     assert float((yr - yn).abs().max()) < 1e-5
     assert rel(outs["new"]["mus_smooth"], outs["ref"]["mus_smooth"]) < 5e-5
     assert rel(outs["new"]["Sigmas_smooth"], outs["ref"]["Sigmas_smooth"]) < 5e-5
+
+
+def test_graphed_train_step_follows_the_eager_trajectory():
+    """kvae_step.GraphedTrainStep (forward + loss + backward + clip + Adam captured in one CUDA graph, replayed) against
+    the eager step body of train.py:32-58 on the same model: same weights, same seed, same batches -> same losses."""
+    dev = torch.device("cuda:0")
+    eager = kvae_step.ReferenceTrainStep(dev, drop_in=True, dynamics_model="lstm", batch=32, T=20, seed=3)
+    graphed = kvae_step.GraphedTrainStep(dev, dynamics_model="lstm", batch=32, T=20, seed=3)
+    init = {k: v.clone() for k, v in eager.model.state_dict().items()}
+    xs = [eager.synthetic_batch(seed=10 + i).to(dev) for i in range(4)]
+    graphed.capture(xs[0])                      # the warm-up inside moved the weights and the Adam state: rewind both
+    graphed.model.load_state_dict(init, strict=True)
+    for st in graphed.opt.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    le, lg = [], []
+    torch.manual_seed(77)
+    for x in xs:
+        le.append(float(eager.step(x)))
+    torch.manual_seed(77)
+    for x in xs:
+        lg.append(float(graphed.step(x)))
+    print("loss trajectories (graphed, eager):", lg, le)
+    for a, b in zip(lg, le):
+        assert abs(a - b) <= 2e-3 * abs(b), (lg, le)
+    assert int(graphed.model.kalman_filter.dyn_params.A.grad is not None)
