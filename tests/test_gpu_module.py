@@ -423,3 +423,45 @@ def test_lstm_mask_after_ones_mask_takes_the_in_kernel_lstm_path():
     assert float((a2 - a3).abs().max()) < 5e-5                           # ... it fed C mu_pred to the LSTM at missing steps
     # (the per-step path runs its LSTM through cuDNN, TF32 GEMMs by default; the in-kernel cell is fp32)
     assert float((o2[0] - o3[0]).norm() / o3[0].norm()) < 5e-4
+
+
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_switch"])
+def test_reference_shaped_calls_replay_from_a_cuda_graph(name, monkeypatch):
+    """smooth() -> elbo() -> autograd.grad captured with torch.cuda.graph (the module makes no host reads under capture:
+    the lazy status checks are skipped) and replayed on NEW input values copied into the static buffers: bit-identical
+    to the eager calls on the same values (bench.py's `e2e` is this route)."""
+    case, _, r32, r64 = load_golden(name)
+    kf, dyn = make_kf(case)
+    stat = {k: case[k].to(DEV).clone() for k in ("Y", "U", "mask", "eps")}
+    monkeypatch.setattr(kf, "_draw_eps", lambda B, T, n, like: stat["eps"])
+
+    def calls():
+        Y = stat["Y"].requires_grad_(True)
+        dyn.reset_state()
+        outs = kf.smooth(Y, stat["U"], stat["mask"])
+        val = kf.elbo(outs[0], outs[1], Y, stat["U"], outs[6], outs[7], outs[8], mask=stat["mask"])
+        gr = torch.autograd.grad(val, [Y, dyn.alpha, dyn.A, dyn.B, dyn.C])
+        return [val, outs[0], outs[1]] + list(gr)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        calls()                                   # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        static_out = calls()
+    stat["Y"].requires_grad_(False)
+    gen = torch.Generator().manual_seed(5)
+    for _ in range(2):                            # new values in the same buffers, then replay
+        with torch.no_grad():
+            stat["Y"].copy_(case["Y"] + 0.05 * torch.randn(case["Y"].shape, generator=gen))
+            stat["eps"].copy_(torch.randn(case["eps"].shape, generator=gen))
+        g.replay()
+        got = [t.clone() for t in static_out]
+        want = calls()
+        stat["Y"].requires_grad_(False)
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b.detach())
