@@ -27,8 +27,11 @@ from .functional import Problem, States, prep
 class _Provenance:
     """What the list tensors returned by filter()/smooth() were made from."""
 
-    def __init__(self, pb, st, diff_inputs, smooth):
+    def __init__(self, pb, st, diff_inputs, smooth, with_grad=False):
         self.pb, self.st, self.diff_inputs, self.smooth = pb, st, diff_inputs, smooth
+        # False: filter()/smooth() ran without autograd (torch.no_grad, or nothing required a gradient): the states and the
+        # list tensors are constants for a later elbo(), exactly as they are in the reference
+        self.with_grad = with_grad
 
 
 def _tag(t, prov):
@@ -207,7 +210,7 @@ class KalmanFilter(nn.Module):
             st, A_list, B_list, C_list = F.smooth_fwd(pb, smooth=smooth, lists=True)
             mf, Sf, mp, Sp = st.mus_filt, st.Sigmas_filt, st.mus_pred, st.Sigmas_pred
             ms, Ss = st.mus_smooth, st.Sigmas_smooth
-        prov = _Provenance(pb, st, diff, smooth)
+        prov = _Provenance(pb, st, diff, smooth, with_grad=needs_grad)
         prov.mus_smooth_ref = weakref.ref(ms) if smooth else None
         prov.Sigmas_smooth_ref = weakref.ref(Ss) if smooth else None
         for t in (A_list, B_list, C_list):
@@ -388,6 +391,11 @@ class KalmanFilter(nn.Module):
             log_q, log_p = dyn.elbo_terms()                                        # :382-383
             extra = (log_p.sum() - log_q.sum()).to(torch.float32)
         Ys, Us, alpha, A, Bm, C, Q = prov.diff_inputs
+        if not prov.with_grad:
+            # the lists (and states) were produced without autograd: constants, as in the reference -- the ELBO then
+            # differentiates only with respect to what THIS call is handed (mu, Sigma, y_t, u_t)
+            fused = False
+            alpha, A, Bm, C, Q = (t.detach() if t is not None else None for t in (alpha, A, Bm, C, Q))
         dev = y_t.device
         if fused:
             # y_t / u_t of this call are the same values as smooth()'s inputs: route the gradient of BOTH uses

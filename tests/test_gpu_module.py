@@ -227,10 +227,9 @@ def test_elbo_general_form_with_filtered_states_and_lists_from_filter():
     Y, U, mask = case["Y"].to(DEV), case["U"].to(DEV), case["mask"].to(DEV)
     eps = case["eps"].to(DEV)
     kf._draw_eps = lambda B, T, n, like: eps
-    with torch.no_grad():
-        mf, Sf, mp, Sp, A_list, B_list, C_list = kf.filter(Y, U, mask)
-    mu_in = mf.clone().requires_grad_(True)
-    Sig_in = Sf.clone().requires_grad_(True)
+    mf, Sf, mp, Sp, A_list, B_list, C_list = kf.filter(Y, U, mask)      # with autograd: the lists carry gradients to alpha/A/C
+    mu_in = mf.detach().clone().requires_grad_(True)
+    Sig_in = Sf.detach().clone().requires_grad_(True)
     Yg = Y.clone().requires_grad_(True)
     val = kf.elbo(mu_in, Sig_in, Yg, U, A_list, B_list, C_list, mask=mask)
     gmu, gSig, gY, gal, gA, gC = torch.autograd.grad(val, [mu_in, Sig_in, Yg, dyn.alpha, dyn.A, dyn.C])
@@ -248,6 +247,31 @@ def test_elbo_general_form_with_filtered_states_and_lists_from_filter():
     for name, got, want in zip(("dmu", "dSigma", "dY", "dalpha", "dA", "dC"), (gmu, gSig, gY, gal, gA, gC), rg):
         want = want.reshape(got.shape) if name != "dSigma" else 0.5 * (want + want.mT)   # kernel returns the symmetric gradient
         assert rel(got, want) < 2e-4, (name, rel(got, want))
+
+
+def test_elbo_after_no_grad_smooth_treats_states_and_lists_as_constants():
+    """Reference semantics: smooth() under torch.no_grad() returns constants, so a later elbo() differentiates
+    only through what it is handed -- y_t (emission term) here -- and nothing reaches alpha / A / B / C."""
+    from oracle import kalman_oracle as ko
+    case, _, _, _ = load_golden("kalman_lstm")
+    kf, dyn = make_kf(case)
+    Y, U, mask = case["Y"].to(DEV), case["U"].to(DEV), case["mask"].to(DEV)
+    eps = case["eps"].to(DEV)
+    kf._draw_eps = lambda B, T, n, like: eps
+    with torch.no_grad():
+        outs = kf.smooth(Y, U, mask)
+    Yg = Y.clone().requires_grad_(True)
+    val = kf.elbo(outs[0], outs[1], Yg, U, outs[6], outs[7], outs[8], mask=mask)
+    gY, gal, gA = torch.autograd.grad(val, [Yg, dyn.alpha, dyn.A], allow_unused=True)
+    assert gal is None and gA is None
+    d = lambda k: case[k].double()
+    Y64 = d("Y").clone().requires_grad_(True)
+    A_seq, B_seq, C_seq, Q_seq = ko.mix(d("alpha"), d("A"), d("B"), d("C"), d("Q"), False, False)
+    ref = ko.elbo(outs[0].detach().cpu().double(), outs[1].detach().cpu().double(), Y64, d("U"), A_seq, B_seq, C_seq, Q_seq,
+                  d("R"), d("mu0"), d("Sigma0"), d("mask"), d("eps"))
+    (rY,) = torch.autograd.grad(ref, [Y64])
+    rel = lambda a, b: float((a.detach().cpu().double() - b).norm() / b.norm())
+    assert rel(val, ref) < 2e-6 and rel(gY, rY) < 2e-4, (rel(val, ref), rel(gY, rY))
 
 
 @pytest.mark.parametrize("shape,hidden", [((4, 2, 4, 3), 50), ((8, 4, 8, 4), 50), ((4, 2, 4, 3), 17)])
