@@ -641,8 +641,6 @@ def e2e_train(cx: Ctx, shape, lanes, steps):
     # ---------------- (1b) the SAME reference-shaped calls, captured once per input slot with torch.cuda.graph and replayed
     # (what a trainer that wants the kernels' speed does with a fixed-shape step; the module makes no host reads under
     # capture).  Per step: the upload of the next inputs, one replay, the copy-back of loss + parameter gradients.
-    if world > 1:
-        return e2e_eager, e2e_engine      # (the NCCL all-reduce of the eager route stays outside a capture)
     torch.cuda.synchronize(dev)
     kf.check_info = False
     graphs, flats = [], []
@@ -668,6 +666,8 @@ def e2e_train(cx: Ctx, shape, lanes, steps):
         upload(i + 1)
         main.wait_event(ev_in[k])
         graphs[k].replay()
+        if world > 1:   # one NCCL all-reduce of the parameter gradients (what allreduce_param_grads does on the eager route)
+            dist.all_reduce(flats[k][1:], op=dist.ReduceOp.SUM)
         out_host[k].copy_(flats[k], non_blocking=True)
         ev_free[k].record(main)
         used[k] = True
@@ -687,8 +687,8 @@ def e2e_train(cx: Ctx, shape, lanes, steps):
            "elbo_last_step": float(out_host[(base[0] - 1) % 2][0]),
            "api": "KalmanFilter.smooth -> .elbo -> torch.autograd.grad (reference signatures) captured once per input slot with "
                   "torch.cuda.graph and replayed; per step: pinned host Y,U,mask,alpha,eps uploaded on a side stream "
-                  "(double-buffered), one replay, loss + parameter gradients copied back to pinned host memory; median of 3 "
-                  "blocks.  The same calls without capture: see e2e_eager",
+                  "(double-buffered), one replay, [N > 1: one NCCL all-reduce of the parameter gradients,] loss + parameter "
+                  "gradients copied back to pinned host memory; median of 3 blocks.  The same calls without capture: see e2e_eager",
            "eager": e2e_eager}
     return e2e, e2e_engine
 
