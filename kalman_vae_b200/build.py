@@ -71,8 +71,28 @@ def _compile(shape_list, obj_dir, lib_path, override_list, verbose=False):
     for name in ("regime", "dp", "vae"):
         o = os.path.join(obj_dir, name + ".o")
         jobs.append(([NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, f"kvae_{name}.cu"), "-o", o], o))
+    # incremental: an object is kept when it is newer than its own .cu, every header and the recorded command line
+    headers = [s for s in _sources() if not s.endswith(".cu")]
+
+    def fresh(job):
+        cmd, obj = job
+        src = [c for c in cmd if c.endswith(".cu")]
+        cmdfile = obj + ".cmd"
+        if not (os.path.exists(obj) and os.path.exists(cmdfile) and open(cmdfile).read() == " ".join(cmd)):
+            return False
+        t = os.path.getmtime(obj)
+        return all(os.path.getmtime(d) <= t for d in headers + src)
+
+    def compile_one(job):
+        if fresh(job):
+            return ""
+        out = _run(job[0], job[1] + ".log")
+        with open(job[1] + ".cmd", "w") as f:
+            f.write(" ".join(job[0]))
+        return out
+
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-        outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
+        outs = list(ex.map(compile_one, jobs))
     if verbose:
         for out in outs:
             sys.stdout.write(out)

@@ -20,8 +20,11 @@ struct DeviceGuard {
 bool variant_ok(const kvae_dims& d) { return (d.q_per_mode != 0) == (d.c_shared != 0); }
 
 // lanes per sequence.  Measured on B200 (profiles/r02_*):
-//  * n = 4, u_dim = 4, T % 4 == 0 and at least 32 768 sequences: ONE lane, i.e. the thread-per-sequence kernels with
+//  * n = 4, u_dim = 4, T % 4 == 0 and at least 12 288 sequences: ONE lane, i.e. the thread-per-sequence kernels with
 //    TMA-staged streams (csrc/kvae_seq.cuh): B = 262 144, T = 20: forward 0.72 ms vs 0.84 ms, adjoint 1.93 vs 2.31 ms.
+//    Crossover measured in profiles/r02_lanes_crossover.log (T = 20, fused step): B = 8 192: 125 us (4 lanes) vs 181 us
+//    (1 lane); 12 288: 219 vs 193; 16 384: 238 vs 203; 32 768: 465 vs 394 (24 576, where the one-lane grid is 1.3 waves,
+//    is the exception: 360 vs 380).
 //  * smaller batches are latency bound (a sequence is a chain of 4 T dependent steps): both families need ~2 000 cycles
 //    per step there; one row per lane (L = n) has more warps to overlap (cfg2, B = 8 192: adjoint 90 vs 130 us).
 //  * n = 16: L = 16 (fewer spills).  n = 8: smallest count that still gives >= 8 warps per SM.
@@ -29,7 +32,7 @@ int pick_lanes(const kvae_dims& d) {
   const int n = d.n;
   if (n > 0 && (n & (n - 1)) != 0)   // z_dim not a power of two: its largest power-of-two divisor (see kvae_shape.cu)
     return (n % 16 == 0) ? 16 : (n % 8 == 0) ? 8 : (n % 4 == 0) ? 4 : (n % 2 == 0) ? 2 : 1;
-  if (n == 4 && d.m == 4 && d.T % 4 == 0 && d.B >= 32768 && !(d.flags & KVAE_FLAG_SMOOTH_ONLY)) return 1;
+  if (n == 4 && d.m == 4 && d.T % 4 == 0 && d.B >= 12288 && !(d.flags & KVAE_FLAG_SMOOTH_ONLY)) return 1;
   if (n <= 4) return n < 1 ? 1 : n;
   if (n != 8) return n;
   const long want_threads = 148L * 8 * 32;

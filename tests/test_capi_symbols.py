@@ -32,7 +32,7 @@ def test_abi_version_and_support_table(lib):
     ok = capi.make_dims(8, 20, 4, 2, 4, 3, False, False, 0)
     assert capi.supported(ok)
     assert capi.pick_lanes(ok) == 4                      # small batch -> widest lane group
-    assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 1   # >= 32768 sequences, T % 4 == 0: thread per sequence
+    assert capi.pick_lanes(capi.make_dims(65536, 1000, 4, 2, 4, 3, False, False, 0)) == 1   # >= 12288 sequences, T % 4 == 0: thread per sequence
     assert capi.pick_lanes(capi.make_dims(65536, 1001, 4, 2, 4, 3, False, False, 0)) == 4   # T % 4 != 0: lane groups
     assert capi.supported(capi.make_dims(8, 20, 16, 8, 16, 8, True, True, 16))
     raw = lambda d: bool(L.kvae_supported(ctypes.byref(d)))
