@@ -709,7 +709,7 @@ def run_impute(cx: Ctx):
     ab = algorithmic_bytes(shape)
     steps = args.steps if args.steps > 0 else 20
     lanes = args.lanes
-    case = make_case(shape, seed=10 + 97 * rank, mask_kind="bernoulli")
+    case = make_case(shape, seed=10 + 97 * rank, mask_kind=args.mask)   # bernoulli(0.5) | block = "observe 4, hide 12" tiled
     g = to_dev(case, dev)
     pb = make_problem(g, shape, lanes)
     B, T, n, p, m, K = pb.shape
@@ -773,7 +773,7 @@ def run_impute(cx: Ctx):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "value_median_of_blocks": full.B * full.T / (statistics.median(blocks) * 1e-3),
             "ms_per_step_blocks": blocks,
-            "config": {"workload": workload_text(name), "lanes_per_sequence": lanes_used, "sequences_per_gpu": B,
+            "config": {"workload": workload_text(name), "mask": args.mask, "lanes_per_sequence": lanes_used, "sequences_per_gpu": B,
                        "l2": f"inputs + outputs of one step = {(ab['fwd'] * B * T) / 2**30:.1f} GiB per GPU (far larger than L2)",
                        "sharding": "batch dimension, contiguous per rank; forward only: no collective", "collective": "none"},
             "checks": {"mask0_mu_filt_equals_mu_pred_bit_exact": ok_mu, "mask0_sigma_filt_equals_sym_sigma_pred_bit_exact": ok_sig,
@@ -875,6 +875,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--mask", default="bernoulli", choices=["bernoulli", "block"],
+                    help="cfg3: the missing-observation pattern (SURVEY 8d: Bernoulli(0.5) per (b,t), or the imputation "
+                         "pattern 'observe 4, hide 12' of kvae/utils/imputation.py:4-25 tiled over T)")
     ap.add_argument("--buffer-sets", type=int, default=6)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -197,15 +197,23 @@ template <int L, int R> struct Group {
 // ---------------------------------------------------------------------------------------
 struct TileRef { float* p; int g; };
 
+// A/B knobs of the n = 4, L = 4 tile layout (see TileGeom): KV_TILE_INTER = 0 selects the group-major layout there too;
+// KV_TILE_RES4 is the residue (mod 32 floats) of its group stride.
+#ifndef KV_TILE_INTER
+#define KV_TILE_INTER 1
+#endif
+#ifndef KV_TILE_RES4
+#define KV_TILE_RES4 4
+#endif
 constexpr int pad_res(int x, int L) {  // smallest y >= x, y % 4 == 0, y % 32 == max(L,4) % 32 (L > 1)
   int y = (x + 3) & ~3;
-  if (L > 1) { const int want = (L < 4 ? 4 : L) % 32; while (y % 32 != want) y += 4; }
+  if (L > 1) { const int want = (L == 4 ? KV_TILE_RES4 : (L < 4 ? 4 : L)) % 32; while (y % 32 != want) y += 4; }
   return y;
 }
 template <int L, int R, int COLS> struct TileGeom {
   static constexpr int ROWS = L * R;
   static constexpr int G = (L == 1) ? 1 : 32 / L;
-  static constexpr bool INTER = (L == 4) && (R == 1) && (COLS <= 4);
+  static constexpr bool INTER = KV_TILE_INTER && (L == 4) && (R == 1) && (COLS <= 4);
   static constexpr int LD = INTER ? G * COLS : ld_of<COLS>::v;
   static constexpr int group_floats = INTER ? ROWS * COLS : pad_res(ROWS * ld_of<COLS>::v, L);
   static constexpr int warp_floats = group_floats * G;
