@@ -18,6 +18,7 @@ and freezing inputs + outputs here.  Two kinds of fixture:
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import torch
@@ -149,6 +150,21 @@ def save_kvae(kind):
     finally:
         ref.switch_mod.gumbel_softmax = orig
     assert torch.equal(out["a_samples"], imp["a_vae"])
+    # fp64 referee: the reference's OWN Kalman block in double on the same (a, u, mask, noise): tells the reference's fp32
+    # rounding floor from an error of the drop-in (tests/_util.check_close)
+    import copy
+    kf64 = copy.deepcopy(model.kalman_filter).double()
+    ref.switch_mod.gumbel_softmax = det_gumbel_softmax
+    try:
+        with torch.no_grad():
+            calls["i"] = 0
+            kf64.dyn_params.reset_state()
+            outs64 = kf64.smooth(out["a_samples"].double().clone(), out["u"].double().clone(), mask=mask.double())
+    finally:
+        ref.switch_mod.gumbel_softmax = orig
+    for k, v in zip(("mus_smooth", "Sigmas_smooth", "mus_filt", "Sigmas_filt", "mus_pred", "Sigmas_pred", "A_list", "B_list",
+                     "C_list"), outs64):
+        arrs["ref64_" + k] = v.detach().contiguous().numpy()
     arrs["a"] = _np(out["a_samples"])
     arrs["mask"] = _np(mask)
     arrs["u"] = _np(out["u"])
@@ -168,9 +184,11 @@ def save_kvae(kind):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # bit-reproducible reductions
-    for name, (shape, kw, with_cot) in KALMAN_CASES.items():
-        save_kalman(name, make_case(shape, **kw), with_cot)
-    save_kalman("kalman_rocket", rocket_case(), False)
+    only_kvae = len(sys.argv) > 1 and sys.argv[1] == "kvae"     # `python oracle/make_golden.py kvae`: the two kvae_* files only
+    if not only_kvae:
+        for name, (shape, kw, with_cot) in KALMAN_CASES.items():
+            save_kalman(name, make_case(shape, **kw), with_cot)
+        save_kalman("kalman_rocket", rocket_case(), False)
     for kind in ("lstm", "switching"):
         save_kvae(kind)
 

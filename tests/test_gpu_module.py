@@ -143,10 +143,9 @@ def test_kvae_imputation_recipe_matches_reference(kind, monkeypatch):
         dyn.reset_state()
         outs = kf.smooth(a.clone(), u.clone(), mask)
     names = OUT_NAMES
-    for k, o in zip(names, outs):
-        ref = g[k]
-        err = float((o.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
-        assert err < 2e-5, (k, err)
+    for k, o in zip(names, outs):   # the reference's fp32 outputs, with its own Kalman block in fp64 as the referee
+        e32, e64, floor = check_close(f"kvae_{kind}.{k}", o, g[k], g["ref64_" + k])
+        print(f"kvae_{kind}.{k}: e32 {e32:.1e} e64 {e64:.1e} floor {floor:.1e}")
     assert torch.allclose(dyn.state_seq.cpu(), g["state_probs"], atol=2e-6)
     a_imputed = (outs[8] @ outs[0]).squeeze(-1)                             # model.py:280-281
     a_filtered = (outs[8] @ outs[2]).squeeze(-1)                            # model.py:287-288
