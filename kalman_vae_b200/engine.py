@@ -295,3 +295,88 @@ class HostPipeline:
     def device_grads(self, k):
         """dY, dalpha (+ parameter-gradient views) of slot k on the device, ordered on the compute stream."""
         return self.steps[k].grads
+
+
+class ImputePipeline:
+    """`KalmanFilter.impute_observations` (the Kalman part of KVAE.impute, model.py:267-288) for inputs that live in pinned
+    HOST memory, chunked over the batch so that the three engines of the step overlap:
+
+        copy stream  : host -> device of chunk c+1 (Y, mask, and alpha / U when given)
+        main stream  : filter + smoother launch of chunk c (forward only, no list tensors, projections emitted by the sweeps)
+        drain stream : device -> host of chunk c-1's `a_imputed` (and `a_filtered`)
+
+    Sequences are independent, so chunking changes no value.  A monolithic call moves inputs, computes and moves results
+    one after the other (BASELINE cfg3: 1.57 GB up, 11 ms of kernels, 0.52 GB down = 48 ms per step on one B200); the
+    pipeline is bound by the larger of the two PCIe directions alone.  `chunk` should stay >= 12 288 sequences where the
+    batch allows it (the thread-per-sequence kernels, see kvae_pick_lanes)."""
+
+    def __init__(self, kf, chunk=16384, want_filtered=False, device=None):
+        self.kf, self.chunk, self.want_filtered = kf, int(chunk), want_filtered
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.drain_stream = torch.cuda.Stream(device=self.dev)
+        self._slots = None
+
+    def _alloc(self, T, p, m, K, has_u, has_alpha):
+        key = (T, p, m, K, has_u, has_alpha)
+        if self._slots is not None and self._key == key:
+            return
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)
+        self._slots = [dict(Y=e(self.chunk, T, p), mask=e(self.chunk, T), U=e(self.chunk, T, m) if has_u else None,
+                            alpha=e(self.chunk, T, K) if has_alpha else None, ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(),
+                            ev_out=torch.cuda.Event(), keep=None, used=False) for _ in range(2)]
+        self._key = key
+
+    @torch.no_grad()
+    def run(self, Y, mask, alpha=None, U=None, out_imputed=None, out_filtered=None):
+        """Y [B,T,p], mask [B,T] (and alpha [B,T,K] for a PrecomputedWeights dynamics object, U [B,T,m]): pinned host tensors.
+        Returns (a_imputed, a_filtered | None) in pinned host memory (the given `out_*` buffers or new ones); blocks until
+        the last chunk has arrived."""
+        kf, dev = self.kf, self.dev
+        B, T, p = Y.shape
+        K = kf.dyn_params.A.size(0)
+        self._alloc(T, p, kf.m, K, U is not None, alpha is not None)
+        if out_imputed is None:
+            out_imputed = torch.empty(B, T, p).pin_memory()
+        if self.want_filtered and out_filtered is None:
+            out_filtered = torch.empty(B, T, p).pin_memory()
+        main = torch.cuda.current_stream(dev)
+        bounds = [(lo, min(lo + self.chunk, B)) for lo in range(0, B, self.chunk)]
+
+        def upload(c):
+            lo, hi = bounds[c]
+            s = self._slots[c % 2]
+            with torch.cuda.stream(self.copy_stream):
+                if s["used"]:
+                    self.copy_stream.wait_event(s["ev_done"])      # the launch that last read this slot's inputs
+                for name, src in (("Y", Y), ("mask", mask), ("U", U), ("alpha", alpha)):
+                    if src is not None:
+                        s[name][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                s["ev_in"].record(self.copy_stream)
+
+        upload(0)
+        for c, (lo, hi) in enumerate(bounds):
+            s = self._slots[c % 2]
+            if c + 1 < len(bounds):
+                upload(c + 1)
+            main.wait_event(s["ev_in"])
+            nb = hi - lo
+            if alpha is not None:
+                kf.dyn_params.set_weights(s["alpha"][:nb])
+            else:
+                kf.dyn_params.reset_state()
+            a_imp, a_filt, _, _ = kf.impute_observations(s["Y"][:nb], None if U is None else s["U"][:nb], s["mask"][:nb])
+            s["ev_done"].record(main)
+            s["keep"] = (a_imp, a_filt)                            # alive until the drain stream is done with them
+            with torch.cuda.stream(self.drain_stream):
+                self.drain_stream.wait_event(s["ev_done"])
+                out_imputed[lo:hi].copy_(a_imp, non_blocking=True)
+                if self.want_filtered:
+                    out_filtered[lo:hi].copy_(a_filt, non_blocking=True)
+                a_imp.record_stream(self.drain_stream)
+                a_filt.record_stream(self.drain_stream)
+                s["ev_out"].record(self.drain_stream)
+            s["used"] = True
+        main.wait_stream(self.drain_stream)
+        self.drain_stream.synchronize()
+        return out_imputed, (out_filtered if self.want_filtered else None)

@@ -131,3 +131,26 @@ def test_two_gpu_data_parallel_matches_single_gpu(collective):
         lo, hi = shard_bounds(301, r, 2)
         for k in ("dY", "dalpha"):
             assert rel(ret[r][k], full[k][lo:hi]) < 2e-5, (r, k)
+
+
+@pytest.mark.parametrize("switching", [False, True])
+def test_impute_pipeline_matches_the_monolithic_call(switching):
+    """engine.ImputePipeline (host-resident inputs, chunks of the batch moving through copy / compute / drain streams)
+    returns exactly what one KalmanFilter.impute_observations call on the whole batch returns; last chunk partial."""
+    from kalman_vae_b200 import KalmanFilter
+    from kalman_vae_b200.dyn_param import PrecomputedWeights
+    from kalman_vae_b200.engine import ImputePipeline
+    dev = torch.device("cuda:0")
+    shape = Shape(300, 24, 4, 2, 4, 3, switching, switching)
+    case = make_case(shape, seed=31, mask_kind="block", zero_u=False, c_std=0.3)
+    dyn = PrecomputedWeights(case["A"], case["B"], case["C"], case["Q"] if switching else None, switching=switching)
+    kf = KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, case["mu0"], case["Sigma0"], dyn).to(dev)
+    host = {k: case[k].float().contiguous().pin_memory() for k in ("Y", "U", "mask", "alpha")}
+    with torch.no_grad():
+        dyn.set_weights(host["alpha"].to(dev))
+        want_i, want_f, _, _ = kf.impute_observations(host["Y"].to(dev), host["U"].to(dev), host["mask"].to(dev))
+    pipe = ImputePipeline(kf, chunk=128, want_filtered=True, device=dev)
+    for _ in range(2):        # second run re-uses the slots
+        got_i, got_f = pipe.run(host["Y"], host["mask"], alpha=host["alpha"], U=host["U"])
+        assert torch.equal(got_i, want_i.cpu()) and torch.equal(got_f, want_f.cpu())
+    assert bool((case["mask"] == 0).any()) and bool(torch.isfinite(got_i).all())
