@@ -641,55 +641,61 @@ def e2e_train(cx: Ctx, shape, lanes, steps):
     # ---------------- (1b) the SAME reference-shaped calls, captured once per input slot with torch.cuda.graph and replayed
     # (what a trainer that wants the kernels' speed does with a fixed-shape step; the module makes no host reads under
     # capture).  Per step: the upload of the next inputs, one replay, the copy-back of loss + parameter gradients.
-    torch.cuda.synchronize(dev)
-    kf.check_info = False
-    graphs, flats = [], []
-    for k in range(2):
-        d = slots[k]
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            Y = d["Y"].requires_grad_(True)
-            dyn.set_weights(d["alpha"].requires_grad_(True))
-            cur_eps[0] = d["eps"]
-            outs = kf.smooth(Y, d["U"], d["mask"])
-            val = kf.elbo(outs[0], outs[1], Y, d["U"], outs[6], outs[7], outs[8], mask=d["mask"])
-            grads = torch.autograd.grad(val, [Y, dyn.alpha] + params_l)
-            flat = torch.cat([val.detach().reshape(1)] + [gr.reshape(-1) for gr in grads[2:]])
-        d["Y"].requires_grad_(False)
-        d["alpha"].requires_grad_(False)
-        graphs.append(g)
-        flats.append(flat)
-    used[0] = used[1] = False
+    try:
+        torch.cuda.synchronize(dev)
+        kf.check_info = False
+        graphs, flats = [], []
+        for k in range(2):
+            d = slots[k]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                Y = d["Y"].requires_grad_(True)
+                dyn.set_weights(d["alpha"].requires_grad_(True))
+                cur_eps[0] = d["eps"]
+                outs = kf.smooth(Y, d["U"], d["mask"])
+                val = kf.elbo(outs[0], outs[1], Y, d["U"], outs[6], outs[7], outs[8], mask=d["mask"])
+                grads = torch.autograd.grad(val, [Y, dyn.alpha] + params_l)
+                flat = torch.cat([val.detach().reshape(1)] + [gr.reshape(-1) for gr in grads[2:]])
+            d["Y"].requires_grad_(False)
+            d["alpha"].requires_grad_(False)
+            graphs.append(g)
+            flats.append(flat)
+        used[0] = used[1] = False
 
-    def graph_step(i):
-        k = i % 2
-        upload(i + 1)
-        main.wait_event(ev_in[k])
-        graphs[k].replay()
-        if world > 1:   # one NCCL all-reduce of the parameter gradients (what allreduce_param_grads does on the eager route)
-            dist.all_reduce(flats[k][1:], op=dist.ReduceOp.SUM)
-        out_host[k].copy_(flats[k], non_blocking=True)
-        ev_free[k].record(main)
-        used[k] = True
+        def graph_step(i):
+            k = i % 2
+            upload(i + 1)
+            main.wait_event(ev_in[k])
+            graphs[k].replay()
+            if world > 1:   # one NCCL all-reduce of the parameter gradients (what allreduce_param_grads does on the eager route)
+                dist.all_reduce(flats[k][1:], op=dist.ReduceOp.SUM)
+            out_host[k].copy_(flats[k], non_blocking=True)
+            ev_free[k].record(main)
+            used[k] = True
 
-    upload(0)
-    for i in range(10):
-        graph_step(i)
-    base[0] = 10
-    blocks_g = []
-    for _ in range(3):
-        blocks_g += cx.timed_blocks(lambda i: graph_step(base[0] + i), n_auto, blocks=1)
-        base[0] += n_auto
-    torch.cuda.synchronize(dev)
-    ms_g = statistics.median(blocks_g)
-    e2e = {"value": world * shape.B * shape.T / (ms_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": ms_g, "ms_per_step_blocks": blocks_g, "steps_per_block": n_auto,
-           "elbo_last_step": float(out_host[(base[0] - 1) % 2][0]),
-           "api": "KalmanFilter.smooth -> .elbo -> torch.autograd.grad (reference signatures) captured once per input slot with "
-                  "torch.cuda.graph and replayed; per step: pinned host Y,U,mask,alpha,eps uploaded on a side stream "
-                  "(double-buffered), one replay, [N > 1: one NCCL all-reduce of the parameter gradients,] loss + parameter "
-                  "gradients copied back to pinned host memory; median of 3 blocks.  The same calls without capture: see e2e_eager",
-           "eager": e2e_eager}
+        upload(0)
+        for i in range(10):
+            graph_step(i)
+        base[0] = 10
+        blocks_g = []
+        for _ in range(3):
+            blocks_g += cx.timed_blocks(lambda i: graph_step(base[0] + i), n_auto, blocks=1)
+            base[0] += n_auto
+        torch.cuda.synchronize(dev)
+        ms_g = statistics.median(blocks_g)
+        e2e = {"value": world * shape.B * shape.T / (ms_g * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_g, "ms_per_step_blocks": blocks_g, "steps_per_block": n_auto,
+               "elbo_last_step": float(out_host[(base[0] - 1) % 2][0]),
+               "api": "KalmanFilter.smooth -> .elbo -> torch.autograd.grad (reference signatures) captured once per input slot with "
+                      "torch.cuda.graph and replayed; per step: pinned host Y,U,mask,alpha,eps uploaded on a side stream "
+                      "(double-buffered), one replay, [N > 1: one NCCL all-reduce of the parameter gradients,] loss + parameter "
+                      "gradients copied back to pinned host memory; median of 3 blocks.  The same calls without capture: see e2e_eager",
+               "eager": e2e_eager}
+    except Exception as err:   # a capture problem must not cost the line: report the eager measurement and say why
+        torch.cuda.synchronize(dev)
+        e2e = dict(e2e_eager)
+        e2e["eager"] = e2e_eager
+        e2e["graph_capture_failed"] = f"{type(err).__name__}: {err}"[:300]
     return e2e, e2e_engine
 
 
@@ -821,7 +827,14 @@ def run_kvae(cx: Ctx):
             stepper = kvae_step.ReferenceTrainStep(device=dev, drop_in=drop_in, seed=10 + rank, distributed=world > 1)
         xs_host = [stepper.synthetic_batch(seed=100 * rank + i).pin_memory() for i in range(4)]
         if graphed:
-            stepper.capture(xs_host[0])
+            try:
+                stepper.capture(xs_host[0])
+            except Exception as err:   # a capture problem must not cost the line: the eager arm below becomes the value
+                res[label] = {"failed": f"{type(err).__name__}: {err}"[:300]}
+                torch.cuda.synchronize(dev)
+                del stepper
+                torch.cuda.empty_cache()
+                continue
             out_host = torch.zeros(1).pin_memory()
 
             def run(i):   # per step: H2D of the frames into the static buffer, replay, D2H of the loss
@@ -841,7 +854,8 @@ def run_kvae(cx: Ctx):
         torch.cuda.empty_cache()
     clocks = cx.sampler.stop() if rank == 0 else None
     if rank == 0:
-        ms = res["drop_in_graphed"]["ms_per_step_blocks"][0]
+        best = "drop_in_graphed" if "ms_per_step" in res["drop_in_graphed"] else "drop_in"
+        ms = res[best]["ms_per_step_blocks"][0]
         value = world * B * T / (ms * 1e-3)
         emit({
             "metric": METRICS["cfg5"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -858,7 +872,7 @@ def run_kvae(cx: Ctx):
                     "api": "the training-step body of kvae/train/train.py:32-58 on the reference KVAE with the drop-in Kalman block; "
                            "the batch of frames comes from pinned host memory every step and the loss is read back"},
             "kvae_step": res,
-            "speedup_over_reference_ops_same_gpu": res["reference_ops"]["ms_per_step"] / res["drop_in_graphed"]["ms_per_step"],
+            "speedup_over_reference_ops_same_gpu": res["reference_ops"]["ms_per_step"] / res[best]["ms_per_step"],
             "speedup_over_reference_ops_same_gpu_eager": res["reference_ops"]["ms_per_step"] / res["drop_in"]["ms_per_step"],
             "gpu_launches": None, "roofline": None, "cpu_baseline": None, "clocks": clocks,
         })
