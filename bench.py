@@ -242,7 +242,7 @@ def run_reference_cfg5(args):
     threads = torch.get_num_threads()
     t0 = time.perf_counter()
     try:
-        stepper = kvae_step.ReferenceTrainStep(device=torch.device("cpu"), drop_in=False, seed=10)
+        stepper = kvae_step.ReferenceTrainStep(device=torch.device("cpu"), drop_in=False, seed=10, dynamics_model=args.dynamics)
     except Exception as err:
         emit({"impl": "reference", "unavailable": f"reference sources not importable: {type(err).__name__}: {err}"[:300]})
         return
@@ -260,7 +260,7 @@ def run_reference_cfg5(args):
     emit({"impl": "reference", "metric": METRICS["cfg5"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
           "dtype": "f32", "data": "synthetic",
-          "config": {"workload": workload_text("cfg5"),
+          "config": {"workload": workload_text("cfg5"), "dynamics_model": args.dynamics,
                      "reference_arm": "the unmodified reference KVAE + its own Kalman filter, torch CPU, all host threads"},
           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                            "sample": f"batch {B} x T={T} per step, mean of {args.steps} steps"},
@@ -822,9 +822,10 @@ def run_kvae(cx: Ctx):
     for label, drop_in in (("drop_in_graphed", True), ("drop_in", True), ("reference_ops", False)):
         graphed = label == "drop_in_graphed"
         if graphed:   # the whole step captured in CUDA graphs (kvae_step.GraphedTrainStep)
-            stepper = kvae_step.GraphedTrainStep(device=dev, seed=10 + rank, distributed=world > 1)
+            stepper = kvae_step.GraphedTrainStep(device=dev, seed=10 + rank, distributed=world > 1, dynamics_model=args.dynamics)
         else:
-            stepper = kvae_step.ReferenceTrainStep(device=dev, drop_in=drop_in, seed=10 + rank, distributed=world > 1)
+            stepper = kvae_step.ReferenceTrainStep(device=dev, drop_in=drop_in, seed=10 + rank, distributed=world > 1,
+                                                   dynamics_model=args.dynamics)
         xs_host = [stepper.synthetic_batch(seed=100 * rank + i).pin_memory() for i in range(4)]
         if graphed:
             try:
@@ -860,7 +861,7 @@ def run_kvae(cx: Ctx):
         emit({
             "metric": METRICS["cfg5"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_text("cfg5"),
+            "config": {"workload": workload_text("cfg5"), "dynamics_model": args.dynamics,
                        "what": "reference KVAE module (conv encoder / decoder in PyTorch) with kalman_vae_b200.KalmanFilter and "
                                "DynamicsParameter swapped in; per step: H2D of the frames, forward, compute_loss, backward, NCCL "
                                "all-reduce of all gradients (N > 1), clip_grad_norm_(10), Adam(lr 0.007).  value = the step captured "
@@ -905,6 +906,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--dynamics", default="lstm", choices=["lstm", "switching"],
+                    help="cfg5: the dynamics parameter network of the KVAE (lstm = KVAE, switching = SKVAE with the regime sampler; "
+                         "the reference's shipped config.yaml:44 selects switching, its KVAEConfig default too)")
     ap.add_argument("--mask", default="bernoulli", choices=["bernoulli", "block"],
                     help="cfg3: the missing-observation pattern (SURVEY 8d: Bernoulli(0.5) per (b,t), or the imputation "
                          "pattern 'observe 4, hide 12' of kvae/utils/imputation.py:4-25 tiled over T)")

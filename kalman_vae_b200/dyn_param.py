@@ -194,7 +194,14 @@ class SwitchingDynamicsParameter(nn.Module):
         from .functional import RegimeSampleFunction
         logits, init_logits = self.markov_regime_posterior(a_seq)
         gumbel = self._draw_gumbel(batch, T, self.K, logits)
-        trans = self.prior.transition_matrix.to(device=dev, dtype=torch.float32)
+        # the prior's transition matrix is a plain (CPU) tensor attribute, as in the reference: keep a device copy instead
+        # of a pageable host-to-device copy per call (which synchronises, and cannot be part of a CUDA-graph capture)
+        tm = self.prior.transition_matrix
+        c = getattr(self, "_trans_dev", None)
+        if c is None or c[0] is not tm or c[1] != tm._version or c[2].device != dev:
+            c = (tm, tm._version, tm.detach().to(device=dev, dtype=torch.float32).contiguous())
+            object.__setattr__(self, "_trans_dev", c)
+        trans = c[2]
         # one launch for the whole chain (and one for its adjoint) instead of ~12 ops per time step
         y_seq, log_q, log_p = RegimeSampleFunction.apply(logits, init_logits, gumbel, trans, float(self.tau), not is_training)
         self.state_seq, self.log_qseq, self.log_pseq = y_seq, log_q, log_p
