@@ -368,14 +368,12 @@ class KalmanFilter(nn.Module):
         """kalman_filter.py:305-401.  The standard-normal draw of `rsample` (:351) is made here with
         the same torch call the reference ends up in (`torch.empty(B,T,n).normal_()`)."""
         prov = getattr(A_list, "_kvae_prov", None)
-        if prov is None or getattr(B_list, "_kvae_prov", None) is not prov:
-            raise NotImplementedError(
-                "elbo(): A_list/B_list/C_list must be the tensors returned by this KalmanFilter's "
-                "filter()/smooth() (the kernels re-mix them from alpha); arbitrary list tensors are not supported yet")
+        if prov is None or getattr(B_list, "_kvae_prov", None) is not prov or Q_list is not None:
+            # list tensors that did not come from this object's filter()/smooth() (the kernels re-mix those from alpha), or
+            # an explicit Q_list: the general form, batched torch ops on the GPU (general_elbo.py), autograd as the reference
+            return self._elbo_given_lists(mu_t_T, Sigma_t_T, y_t, u_t, A_list, B_list, C_list, Q_list, mask)
         pb, st = prov.pb, prov.st
         B, T, n = pb.dims.B, pb.dims.T, pb.dims.n
-        if Q_list is not None:
-            raise NotImplementedError("elbo(): explicit Q_list is not supported; Q is mixed from alpha in the kernel")
         mask_t = self._mask(mask, B, T, y_t)
         # fast path: the states are the smoothed states of the SAME smooth() call as the lists, on the same y/mask
         fused = (prov.smooth and prov.mus_smooth_ref() is mu_t_T and prov.Sigmas_smooth_ref() is Sigma_t_T)
@@ -444,6 +442,25 @@ class KalmanFilter(nn.Module):
                 break
         self.last_chol = dict(jitter_smooth=js, jitter_q=jq, diag_smooth=ds, diag_q=dq)
         return val
+
+    def _elbo_given_lists(self, mu, Sigma, y_t, u_t, A_list, B_list, C_list, Q_list, mask):
+        from .general_elbo import elbo_given_lists
+        dyn = self.dyn_params
+        Bsz, T = y_t.shape[0], y_t.shape[1]
+        if Q_list is None:                                                         # kalman_filter.py:342-345
+            Q_list = getattr(dyn, "Q_seq", None)
+            if Q_list is None and dyn.is_switching_dynamics and getattr(dyn, "state_seq", None) is not None:
+                # the mirrors do not materialise Q_seq (switch_dyn_param.py:84): mix it from the last regime weights
+                Q_list = torch.einsum("btk,kij->btij", dyn.state_seq, dyn.Q)
+            if Q_list is None:
+                Q_list = self.Q
+        extra = None
+        if dyn.is_switching_dynamics:
+            log_q, log_p = dyn.elbo_terms()                                        # :382-383
+            extra = log_p.sum() - log_q.sum()
+        eps = self._draw_eps(Bsz, T, self.n, y_t)
+        return elbo_given_lists(mu, Sigma, y_t, u_t, A_list, B_list, C_list, Q_list, self.R, self.mu0, self.Sigma0,
+                                self._mask(mask, Bsz, T, y_t), eps, extra)
 
     def _draw_eps(self, B, T, n, like):
         """The standard-normal draw behind MultivariateNormal.rsample (kalman_filter.py:351)."""

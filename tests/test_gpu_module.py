@@ -488,3 +488,49 @@ def test_reference_shaped_calls_replay_from_a_cuda_graph(name, monkeypatch):
         torch.cuda.synchronize()
         for a, b in zip(got, want):
             assert torch.equal(a, b.detach())
+
+
+@pytest.mark.parametrize("name,with_q", [("kalman_lstm", False), ("kalman_lstm", True), ("kalman_switch", False)])
+def test_elbo_with_foreign_lists_and_explicit_q_list(name, with_q):
+    """elbo() with list tensors that are NOT this object's outputs (here: perturbed copies) and with an explicit Q_list
+    (kalman_filter.py:342-345): the general form (general_elbo.py), value and gradients w.r.t. the lists, mu, Sigma, y
+    against the oracle's restatement of :305-401 in fp64."""
+    from oracle import kalman_oracle as ko
+    case, _, _, _ = load_golden(name)
+    kf, dyn = make_kf(case)
+    Y, U, mask = case["Y"].to(DEV), case["U"].to(DEV), case["mask"].to(DEV)
+    eps = case["eps"].to(DEV)
+    kf._draw_eps = lambda B, T, n, like: eps
+    with torch.no_grad():
+        dyn.reset_state()
+        outs = kf.smooth(Y, U, mask)
+    gen = torch.Generator().manual_seed(3)
+    pert = lambda t: (t.detach().cpu() * (1.0 + 0.05 * torch.randn(t.shape, generator=gen))).contiguous()
+    host = dict(mu=outs[0].detach().cpu(), Sig=outs[1].detach().cpu(), A=pert(outs[6]), B=pert(outs[7]), C=pert(outs[8].contiguous()))
+    Bsz, T, n = host["mu"].shape[:3]
+    Qh = None
+    if with_q:
+        W = 0.1 * torch.randn(Bsz, T, n, n, generator=gen)
+        Qh = 0.02 * torch.eye(n) + W @ W.mT
+    dev_in = {k: v.to(DEV).requires_grad_(True) for k, v in host.items()}
+    Yg = Y.clone().requires_grad_(True)
+    Qd = None if Qh is None else Qh.to(DEV).requires_grad_(True)
+    val = kf.elbo(dev_in["mu"], dev_in["Sig"], Yg, U, dev_in["A"], dev_in["B"], dev_in["C"], Q_list=Qd, mask=mask)
+    leaves = [dev_in[k] for k in ("mu", "Sig", "A", "B", "C")] + [Yg] + ([Qd] if with_q else [])
+    got = torch.autograd.grad(val, leaves)
+    # oracle, fp64
+    d = lambda k: case[k].double()
+    o = {k: v.double().requires_grad_(True) for k, v in host.items()}
+    Y64 = d("Y").clone().requires_grad_(True)
+    if with_q:
+        Q64 = Qh.double().requires_grad_(True)
+    elif case["q_per_mode"]:
+        Q64 = torch.einsum("btk,kij->btij", d("alpha"), d("Q"))
+    else:
+        Q64 = d("Q").expand(Bsz, T, n, n)
+    ref = ko.elbo(o["mu"], o["Sig"], Y64, d("U"), o["A"], o["B"], o["C"], Q64, d("R"), d("mu0"), d("Sigma0"), d("mask"), d("eps"))
+    want = torch.autograd.grad(ref, [o[k] for k in ("mu", "Sig", "A", "B", "C")] + [Y64] + ([Q64] if with_q else []))
+    rel = lambda a, b: float((a.detach().cpu().double() - b).norm() / b.norm().clamp_min(1e-30))
+    assert rel(val, ref) < 5e-6, rel(val, ref)
+    for nm, a, b in zip(("dmu", "dSigma", "dA", "dB", "dC", "dY", "dQ"), got, want):
+        assert rel(a, b.reshape(a.shape)) < 2e-4, (nm, rel(a, b.reshape(a.shape)))
