@@ -113,8 +113,9 @@ class KalmanFilter(nn.Module):
                 if kind == "mask":
                     raise NotImplementedError(
                         "an earlier filter()/smooth() call with lstm dynamics and gradients enabled had missing observations "
-                        "(mask != 1): that combination is forward-only here (the reference feeds C mu_pred to the LSTM at "
-                        "missing steps, kalman_filter.py:183-185); wrap such calls in torch.no_grad()")
+                        "(mask != 1): the batched-alpha kernels equal the reference only for fully observed sequences (it feeds "
+                        "C mu_pred to the LSTM at missing steps, kalman_filter.py:183-185).  Set kf.strict = True to have such "
+                        "calls take the step-by-step autograd path (general_steps.py), or wrap them in torch.no_grad()")
                 raise torch.linalg.LinAlgError(
                     "kvae: a factorisation in an earlier elbo() call met a non-positive pivot (status word "
                     f"{code}); construct KalmanFilter(..., check_info=True) to get the reference's jitter ladder "
@@ -188,9 +189,10 @@ class KalmanFilter(nn.Module):
             bad = (mask_t != 1).any()
             if self.strict:
                 if bool(bad.item()):
-                    raise NotImplementedError(
-                        "lstm dynamics with missing observations is forward-only here (imputation, as in "
-                        "KVAE.impute); wrap the call in torch.no_grad()")
+                    # missing observations under autograd: the reference's own step-by-step loop in torch ops (the gradient
+                    # has to pass through the LSTM between the steps); not a kernel path (general_steps.py)
+                    from .general_steps import filter_smooth_stepwise
+                    return filter_smooth_stepwise(self, Y, U, mask_t, smooth)
             else:
                 self._defer(bad, "mask")
         alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
@@ -483,11 +485,18 @@ class KalmanFilter(nn.Module):
 
     def filter_step(self, mu_t_t, Sigma_t_t, y_t, u_t, A, B, C, Q, mask_t=None):
         """kalman_filter.py:31-104 — one predict/update step with explicit per-sample matrices.
-        Returns (mu_t_t [B,n,1], Sigma_t_t, mu_t_tprev [B,n,1], Sigma_t_tprev, A, B, C).  Forward only."""
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (mu_t_t, Sigma_t_t, y_t, u_t, A, B, C)):
-            raise NotImplementedError("filter_step is forward-only here; differentiate through filter()/smooth()")
+        Returns (mu_t_t [B,n,1], Sigma_t_t, mu_t_tprev [B,n,1], Sigma_t_tprev, A, B, C).  One kernel launch; when a
+        gradient is wanted: batched torch ops under autograd (general_steps.py)."""
         batch = y_t.size(0)
         n, m, p = self.n, self.m, self.p
+        if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (mu_t_t, Sigma_t_t, y_t, u_t, A, B, C, Q)):
+            from .general_steps import filter_step_ops
+            if not y_t.is_cuda:
+                raise F.capi.KvaeError("KalmanFilter (B200-native) needs CUDA tensors; there is no CPU path")
+            mk = None if mask_t is None else (mask_t.expand(batch) if mask_t.dim() == 0 else mask_t.reshape(batch))
+            mu_f, Sig_f, mu_p, Sig_p = filter_step_ops(mu_t_t.reshape(batch, n, 1), Sigma_t_t, y_t.reshape(batch, p, 1),
+                                                      u_t.reshape(batch, m, 1), A, B, C, Q, self.R.to(y_t.dtype), mk)
+            return mu_f, Sig_f, mu_p, Sig_p, A, B, C
         dev = y_t.device
         f = lambda x, *shape: x.detach().to(torch.float32).expand(*shape).contiguous().view(*shape)
         Qd = f(Q, batch, n, n).view(batch, 1, n, n)                                  # :35-36 (2-d Q is expanded)
@@ -505,12 +514,17 @@ class KalmanFilter(nn.Module):
                 st.Sigmas_pred.view(batch, n, n), A, B, C)
 
     def smooth_step(self, Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, mu_t_t, mu_tpost_t, mu_tpost_T, A):
-        """kalman_filter.py:204-237 — one RTS step.  Returns (mu_t_T [B,n,1], Sigma_t_T).  Forward only."""
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, mu_t_t,
-                                                                     mu_tpost_t, mu_tpost_T, A)):
-            raise NotImplementedError("smooth_step is forward-only here; differentiate through smooth()")
+        """kalman_filter.py:204-237 — one RTS step.  Returns (mu_t_T [B,n,1], Sigma_t_T).  One kernel launch; when a
+        gradient is wanted: batched torch ops under autograd (general_steps.py)."""
         batch = Sigma_t_t.size(0)
         n, m, p = self.n, self.m, self.p
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, mu_t_t,
+                                                                     mu_tpost_t, mu_tpost_T, A)):
+            from .general_steps import smooth_step_ops
+            if not Sigma_t_t.is_cuda:
+                raise F.capi.KvaeError("KalmanFilter (B200-native) needs CUDA tensors; there is no CPU path")
+            r3 = lambda v: v.reshape(batch, n, 1)
+            return smooth_step_ops(Sigma_t_t, Sigma_tpost_t, Sigma_tpost_T, r3(mu_t_t), r3(mu_tpost_t), r3(mu_tpost_T), A)
         dev = Sigma_t_t.device
         f32 = lambda x: x.detach().to(torch.float32)
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)

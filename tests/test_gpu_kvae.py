@@ -150,3 +150,50 @@ def test_graphed_train_step_switching_dynamics():
     st.check()
     assert all(l == l and abs(l) < 1e9 for l in losses), losses
     assert min(losses[4:]) < losses[0], losses
+
+
+def test_lstm_dynamics_with_missing_observations_under_autograd_matches_reference():
+    """kf.strict = True: lstm dynamics + a mask with zeros + gradients wanted takes the step-by-step autograd path
+    (general_steps.py; the gradient passes through the LSTM between the steps).  Against the reference's own KalmanFilter
+    + DynamicsParameter on the same GPU with the same weights: the nine outputs, the ELBO and the gradients w.r.t. the
+    observations, A, B, C and the LSTM / head weights."""
+    import kalman_vae_b200
+    from kalman_vae_b200.synthetic import Shape, make_case
+    model_mod, _ = kvae_step.load_reference_model_module()
+    dev = torch.device("cuda:0")
+    case = make_case(Shape(24, 12, 4, 2, 4, 3), seed=4, mask_kind="block", zero_u=False, c_std=0.3)
+    assert bool((case["mask"] == 0).any())
+    g = lambda k: case[k].to(dev).float()
+    torch.manual_seed(11)
+    ref_dyn = model_mod.base_dyn_param.DynamicsParameter(g("A"), g("B"), g("C")).to(dev)
+    new_dyn = kalman_vae_b200.DynamicsParameter(g("A"), g("B"), g("C")).to(dev)
+    with torch.no_grad():   # a head that actually mixes the modes
+        ref_dyn.head_w.bias.copy_(torch.tensor([0.0, -0.5, 0.3], device=dev))
+    new_dyn.load_state_dict(ref_dyn.state_dict(), strict=True)
+    ref_kf = model_mod.KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, g("mu0"), g("Sigma0"), ref_dyn).to(dev)
+    new_kf = kalman_vae_b200.KalmanFilter(0.02 ** 0.5, 0.03 ** 0.5, g("mu0"), g("Sigma0"), new_dyn).to(dev)
+    new_kf.strict = True
+    eps = torch.randn(24, 12, 4, device=dev)
+    res = {}
+    for tag, kf, dyn in (("ref", ref_kf, ref_dyn), ("new", new_kf, new_dyn)):
+        Y = g("Y").requires_grad_(True)
+        dyn.reset_state()
+        outs = kf.smooth(Y, g("U"), g("mask"))
+        if tag == "new":
+            kf._draw_eps = lambda B, T, n, like: eps
+            val = kf.elbo(outs[0], outs[1], Y, g("U"), outs[6], outs[7], outs[8], mask=g("mask"))
+        else:   # the reference draws inside MultivariateNormal.rsample: inject the same standard-normal draw
+            import torch.distributions as D
+            orig = D.MultivariateNormal.rsample
+            D.MultivariateNormal.rsample = lambda self, sample_shape=torch.Size(): self.loc + (self._unbroadcasted_scale_tril @ eps.unsqueeze(-1)).squeeze(-1)
+            try:
+                val = kf.elbo(outs[0], outs[1], Y, g("U"), outs[6], outs[7], outs[8], mask=g("mask"))
+            finally:
+                D.MultivariateNormal.rsample = orig
+        params = [Y, dyn.A, dyn.B, dyn.C, dyn.lstm.weight_ih_l0, dyn.lstm.weight_hh_l0, dyn.head_w.weight]
+        res[tag] = ([o.detach() for o in outs], val.detach(), torch.autograd.grad(val, params))
+    for a, b in zip(res["new"][0], res["ref"][0]):
+        assert rel(a, b) < 2e-5, rel(a, b)
+    assert abs(float(res["new"][1]) - float(res["ref"][1])) <= 2e-5 * abs(float(res["ref"][1]))
+    for nm, a, b in zip(("dY", "dA", "dB", "dC", "dW_ih", "dW_hh", "dW_head"), res["new"][2], res["ref"][2]):
+        assert rel(a, b) < 2e-3, (nm, rel(a, b))

@@ -534,3 +534,43 @@ def test_elbo_with_foreign_lists_and_explicit_q_list(name, with_q):
     assert rel(val, ref) < 5e-6, rel(val, ref)
     for nm, a, b in zip(("dmu", "dSigma", "dA", "dB", "dC", "dY", "dQ"), got, want):
         assert rel(a, b.reshape(a.shape)) < 2e-4, (nm, rel(a, b.reshape(a.shape)))
+
+
+def test_filter_step_and_smooth_step_under_autograd():
+    """filter_step / smooth_step with tensors that require a gradient (general_steps.py): values equal the kernel forms
+    (forward-only) and the gradients equal autograd of the oracle's restatement in fp64."""
+    from oracle import kalman_oracle as ko
+    case, _, r32, r64 = load_golden("kalman_lstm")
+    kf, dyn = make_kf(case)
+    B, T, n = case["Y"].shape[0], case["Y"].shape[1], kf.n
+    t = 3
+    d = lambda x: x.to(DEV).float()
+    A_t, B_t, C_t = d(r32["A_list"][:, t]), d(r32["B_list"][:, t]), d(r32["C_list"][:, t])
+    mu_prev, Sig_prev = d(r32["mus_filt"][:, t - 1]), d(r32["Sigmas_filt"][:, t - 1])
+    y_t, u_t, m_t = d(case["Y"][:, t]), d(case["U"][:, t]), d(case["mask"][:, t])
+    with torch.no_grad():
+        k_out = kf.filter_step(mu_prev, Sig_prev, y_t, u_t, A_t, B_t, C_t, kf.Q, mask_t=m_t)
+    leaves = [x.clone().requires_grad_(True) for x in (mu_prev, Sig_prev, y_t, A_t, C_t)]
+    g_out = kf.filter_step(leaves[0], leaves[1], leaves[2], u_t, leaves[3], B_t, leaves[4], kf.Q, mask_t=m_t)
+    for a, b in zip(g_out[:4], k_out[:4]):
+        assert float((a - b).norm() / b.norm()) < 2e-6
+    w = [torch.randn_like(o) for o in g_out[:4]]
+    got = torch.autograd.grad(sum((wi * o).sum() for wi, o in zip(w, g_out[:4])), leaves)
+    l64 = [x.detach().cpu().double().requires_grad_(True) for x in (mu_prev, Sig_prev, y_t, A_t, C_t)]
+    o64 = ko.filter_step(l64[0], l64[1], l64[2].unsqueeze(-1), u_t.cpu().double().unsqueeze(-1), l64[3], B_t.cpu().double(),
+                         l64[4], kf.Q.cpu().double(), kf.R.cpu().double().expand(B, -1, -1), m_t.cpu().double())
+    want = torch.autograd.grad(sum((wi.cpu().double() * o).sum() for wi, o in zip(w, o64)), l64)
+    rel = lambda a, b: float((a.detach().cpu().double() - b).norm() / b.norm().clamp_min(1e-30))
+    for nm, a, b in zip(("dmu", "dSigma", "dy", "dA", "dC"), got, want):
+        assert rel(a, b) < 2e-4, (nm, rel(a, b))
+    # smooth_step
+    Sf, Sp1, Ss1 = d(r32["Sigmas_filt"][:, t]), d(r32["Sigmas_pred"][:, t + 1]), d(r32["Sigmas_smooth"][:, t + 1])
+    mf, mp1, ms1 = d(r32["mus_filt"][:, t]), d(r32["mus_pred"][:, t + 1]), d(r32["mus_smooth"][:, t + 1])
+    A1 = d(r32["A_list"][:, t + 1])
+    with torch.no_grad():
+        km, kS = kf.smooth_step(Sf, Sp1, Ss1, mf, mp1, ms1, A1)
+    Sfg = Sf.clone().requires_grad_(True)
+    gm, gS = kf.smooth_step(Sfg, Sp1, Ss1, mf, mp1, ms1, A1)
+    assert float((gm - km).norm() / km.norm()) < 2e-6 and float((gS - kS).norm() / kS.norm()) < 2e-6
+    assert torch.autograd.grad(gS.sum() + gm.sum(), [Sfg])[0].isfinite().all()
+    check_close("smooth_step.Sigma", gS, r32["Sigmas_smooth"][:, t], r64["Sigmas_smooth"][:, t])
