@@ -196,4 +196,5 @@ def test_lstm_dynamics_with_missing_observations_under_autograd_matches_referenc
         assert rel(a, b) < 2e-5, rel(a, b)
     assert abs(float(res["new"][1]) - float(res["ref"][1])) <= 2e-5 * abs(float(res["ref"][1]))
     for nm, a, b in zip(("dY", "dA", "dB", "dC", "dW_ih", "dW_hh", "dW_head"), res["new"][2], res["ref"][2]):
-        assert rel(a, b) < 2e-3, (nm, rel(a, b))
+        print(f"lstm + mask under autograd, {nm}: rel {rel(a, b):.1e}")
+        assert rel(a, b) < 2e-4, (nm, rel(a, b))      # measured: 1e-7 .. 2e-5
