@@ -39,15 +39,21 @@ def smooth_step_ops(Sigma_f, Sigma_p1, Sigma_s1, mu_f, mu_p1, mu_s1, A1):
     return mu_s, 0.5 * (Sig_s + Sig_s.transpose(-1, -2))                      # :235
 
 
-def filter_smooth_stepwise(kf, Y, U, mask, smooth):
-    """filter() / smooth() for lstm dynamics with missing observations UNDER AUTOGRAD: the reference's loop
-    (kalman_filter.py:141-191 and :250-271) step by step, the dynamics network called between the steps."""
+def filter_smooth_stepwise(kf, Y, U, mask, smooth, weights=None):
+    """filter() / smooth() step by step in torch ops: the reference's loop (kalman_filter.py:141-191 and :250-271).
+    weights = None: lstm dynamics, the dynamics network called between the steps (missing observations under autograd).
+    weights = (alpha [B,T,K], A, B, C, Q, q_per_mode, c_shared): mixture weights known up front (switching dynamics, or
+    any dynamics in a dtype the kernels do not compute in, e.g. float64)."""
     dyn = kf.dyn_params
     Bsz, T, p = Y.shape
     n, m = kf.n, kf.m
     dev, dt = Y.device, Y.dtype
     if U is None:
         U = torch.zeros(Bsz, T, m, device=dev, dtype=dt)
+    if mask is None:
+        mask = torch.ones(Bsz, T, device=dev, dtype=dt)
+    if weights is not None:
+        return _filter_smooth_given_weights(kf, Y, U, mask, smooth, *weights)
     mu = kf.mu0.to(dt).expand(Bsz, n).unsqueeze(-1)
     Sig = kf.Sigma0.to(dt).expand(Bsz, n, n)
     R = kf.R.to(dt)
@@ -76,4 +82,34 @@ def filter_smooth_stepwise(kf, Y, U, mask, smooth):
     ms[-1], Ss[-1] = mf[:, -1], Sf[:, -1]                                     # :251-256 (copied, not symmetrised)
     for t in range(T - 2, -1, -1):
         ms[t], Ss[t] = smooth_step_ops(Sf[:, t], Sp[:, t + 1], Ss[t + 1], mf[:, t], mp[:, t + 1], ms[t + 1], A_list[:, t + 1])   # :258
+    return st(ms), st(Ss), mf, Sf, mp, Sp, A_list, B_list, C_list
+
+
+def _filter_smooth_given_weights(kf, Y, U, mask, smooth, alpha, A, Bm, C, Q, q_per_mode, c_shared):
+    Bsz, T, p = Y.shape
+    n = kf.n
+    dt = Y.dtype
+    A_list = torch.einsum("btk,kij->btij", alpha, A.to(dt))                   # dyn_param.py:58-60 / switch_dyn_param.py:82-84
+    B_list = torch.einsum("btk,kij->btij", alpha, Bm.to(dt))
+    C_list = C[0].to(dt).expand(Bsz, T, -1, -1) if c_shared else torch.einsum("btk,kij->btij", alpha, C.to(dt))   # :85-86
+    Q_seq = torch.einsum("btk,kij->btij", alpha, Q.to(dt)) if q_per_mode else None
+    mu = kf.mu0.to(dt).expand(Bsz, n).unsqueeze(-1)
+    Sig = kf.Sigma0.to(dt).expand(Bsz, n, n)
+    R = kf.R.to(dt)
+    mf, Sf, mp, Sp = [], [], [], []
+    for t in range(T):
+        Qt = Q_seq[:, t] if q_per_mode else Q.to(dt)
+        mu, Sig, mu_p, Sig_p = filter_step_ops(mu, Sig, Y[:, t].unsqueeze(-1), U[:, t].unsqueeze(-1), A_list[:, t], B_list[:, t],
+                                               C_list[:, t], Qt, R, mask[:, t])
+        mf.append(mu); Sf.append(Sig); mp.append(mu_p); Sp.append(Sig_p)
+    st = lambda xs: torch.stack(xs, 1)
+    mf, Sf, mp, Sp = st(mf), st(Sf), st(mp), st(Sp)
+    if q_per_mode:
+        kf.dyn_params.Q_seq = Q_seq                                           # switch_dyn_param.py:84 side effect
+    if not smooth:
+        return mf, Sf, mp, Sp, A_list, B_list, C_list
+    ms, Ss = [None] * T, [None] * T
+    ms[-1], Ss[-1] = mf[:, -1], Sf[:, -1]
+    for t in range(T - 2, -1, -1):
+        ms[t], Ss[t] = smooth_step_ops(Sf[:, t], Sp[:, t + 1], Ss[t + 1], mf[:, t], mp[:, t + 1], ms[t + 1], A_list[:, t + 1])
     return st(ms), st(Ss), mf, Sf, mp, Sp, A_list, B_list, C_list

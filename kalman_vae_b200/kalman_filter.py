@@ -176,6 +176,16 @@ class KalmanFilter(nn.Module):
         mask_t = self._mask(mask, B, T, Y)
         dyn = self.dyn_params
         self._poll_deferred()
+        if Y.dtype != torch.float32:
+            # the kernels compute in fp32; the reference runs in whatever dtype its buffers have (float64 works there,
+            # SURVEY 8 a1): other dtypes take the step-by-step torch-op route in that dtype (general_steps.py)
+            if not Y.is_cuda:
+                raise F.capi.KvaeError("KalmanFilter (B200-native) needs CUDA tensors; there is no CPU path")
+            from .general_steps import filter_smooth_stepwise
+            if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and mask_t is not None:
+                return filter_smooth_stepwise(self, Y, U, mask_t, smooth)      # alpha depends on the running prediction
+            alpha, A, Bm, C, Q, qpm, csh = self._weights(Y, mask_t)
+            return filter_smooth_stepwise(self, Y, U, mask_t, smooth, weights=(alpha.to(Y.dtype), A, Bm, C, Q, qpm, csh))
         if (not dyn.is_switching_dynamics) and dyn.K > 1 and hasattr(dyn, "lstm") and mask_t is not None:
             # lstm dynamics + a mask: alpha_{t+1} depends on the running prediction wherever mask_t = 0
             # (kalman_filter.py:159,183-185).  No host look at the mask's values:

@@ -574,3 +574,30 @@ def test_filter_step_and_smooth_step_under_autograd():
     assert float((gm - km).norm() / km.norm()) < 2e-6 and float((gS - kS).norm() / kS.norm()) < 2e-6
     assert torch.autograd.grad(gS.sum() + gm.sum(), [Sfg])[0].isfinite().all()
     check_close("smooth_step.Sigma", gS, r32["Sigmas_smooth"][:, t], r64["Sigmas_smooth"][:, t])
+
+
+@pytest.mark.parametrize("name", ["kalman_lstm", "kalman_switch"])
+def test_float64_module_takes_the_torch_route(name):
+    """The reference computes in the dtype of its buffers (float64 works there).  The kernels are fp32: a float64 module /
+    float64 inputs take the step-by-step torch-op route (general_steps.py, general_elbo.py) and return float64 results that
+    match the reference's fp64 goldens to 1e-9 (outputs, ELBO, gradients)."""
+    case, cot, r32, r64 = load_golden(name)
+    kf, dyn = make_kf(case)
+    kf, dyn = kf.double(), dyn.double()
+    Y = case["Y"].to(DEV).double().requires_grad_(True)
+    U, mask, eps = case["U"].to(DEV).double(), case["mask"].to(DEV).double(), case["eps"].to(DEV).double()
+    dyn.reset_state()
+    outs = kf.smooth(Y, U, mask)
+    rel = lambda a, b: float((a.detach().cpu().double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    for k, o in zip(OUT_NAMES, outs):
+        assert o.dtype == torch.float64 and rel(o, r64[k]) < 1e-9, (k, rel(o, r64[k]))
+    kf._draw_eps = lambda B, T, n, like: eps
+    val = kf.elbo(outs[0], outs[1], Y, U, outs[6], outs[7], outs[8], mask=mask)
+    assert val.dtype == torch.float64 and rel(val, r64["elbo"]) < 1e-9
+    loss = val
+    if cot:   # the goldens' gradients are those of elbo + sum <cotangent, output>
+        for k, o in zip(OUT_NAMES, outs):
+            if k in cot:
+                loss = loss + (cot[k].to(DEV).double() * o).sum()
+    gY, gA = torch.autograd.grad(loss, [Y, dyn.A])
+    assert rel(gY, r64["dY"]) < 1e-7 and rel(gA, r64["dA"]) < 1e-7, (rel(gY, r64["dY"]), rel(gA, r64["dA"]))
