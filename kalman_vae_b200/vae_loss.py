@@ -90,7 +90,7 @@ def vae_loss(x, x_mu, x_var, a, a_mu, a_var, scale_reconstruction: float = 0.3, 
         pixels *= int(s)
     xv = float(x_var) if not torch.is_tensor(x_var) else (float(x_var.item()) if x_var.numel() == 1 else None)
     if xv is None:
-        raise NotImplementedError("vae_loss: only a scalar x_var is supported")
+        return _vae_loss_per_pixel_variance(x, x_mu, x_var, a, a_mu, a_var, scale_reconstruction, beta, mask, out_distr)
     m = None
     if mask is not None:
         m = mask.to(device=x.device, dtype=torch.float32)
@@ -128,3 +128,22 @@ def reparameterize(mu, var, eps=None):
     if eps is None:
         eps = torch.randn_like(var)
     return _Reparam.apply(mu, var, eps)
+
+
+def _vae_loss_per_pixel_variance(x, x_mu, x_var, a, a_mu, a_var, scale_reconstruction, beta, mask, out_distr):
+    """losses.py:62-111 for a TENSOR-valued x_var (one variance per pixel; KVAE.compute_loss passes a scalar and runs in
+    the reduction kernel above): plain torch ops under autograd -- a library route beside the kernel path."""
+    import math
+    B, T = x.shape[:2]
+    m = torch.ones(B, T, dtype=x.dtype, device=x.device) if mask is None else mask.to(device=x.device, dtype=x.dtype).view(B, T)
+    logn = lambda v, mean, var: -0.5 * math.log(2.0 * math.pi) - 0.5 * torch.log(var) - (v - mean) ** 2 / (2.0 * var)   # :5-17
+    if out_distr.lower() == "bernoulli":
+        per_frame = -torch.nn.functional.binary_cross_entropy_with_logits(x_mu, x, reduction="none").flatten(2).sum(-1)   # :83-85
+    else:
+        per_frame = logn(x, x_mu, x_var).flatten(2).sum(-1)
+    denom = m.sum().clamp(min=1.0)                                                   # :81
+    recon = (per_frame * m).sum() / denom
+    log_q = logn(a, a_mu, a_var).sum(-1)
+    log_p = (-0.5 * math.log(2.0 * math.pi) - 0.5 * a * a).sum(-1)                   # standard-normal prior, :96-99
+    reg = ((log_p - log_q) * m).sum() / denom                                        # :103-105
+    return scale_reconstruction * recon + beta * reg, recon, reg                     # :107-109

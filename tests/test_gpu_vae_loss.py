@@ -58,3 +58,22 @@ def test_reparameterize_matches_model():
     assert float((a.cpu().double() - a64).norm() / a64.norm()) < 1e-6
     assert float((gm.cpu().double() - gm64).norm() / gm64.norm()) < 1e-6
     assert float((gv.cpu().double() - gv64).norm() / gv64.norm()) < 1e-6
+
+
+def test_vae_loss_per_pixel_variance_takes_the_torch_route():
+    """A tensor-valued x_var (one variance per pixel) is outside the reduction kernel: torch ops under autograd, against the
+    oracle restatement in fp64."""
+    dev = torch.device("cuda:0")
+    x, x_mu, a, a_mu, a_var, mask = _inputs(5, B=4, T=6)
+    g = torch.Generator().manual_seed(9)
+    x_var = 0.05 + torch.rand(x.shape, generator=g)
+    kw = dict(scale_reconstruction=0.3, beta=0.7, out_distr="gaussian")
+    l64 = [t.double().requires_grad_(True) for t in (x_mu, a, x_var)]
+    want = vo.vae_loss(x.double(), l64[0], l64[2], l64[1], a_mu.double(), a_var.double(), mask=mask.double(), **kw)
+    gw = torch.autograd.grad(want[0], l64)
+    lv = [t.to(dev).requires_grad_(True) for t in (x_mu, a, x_var)]
+    got = vae_loss(x.to(dev), lv[0], lv[2], lv[1], a_mu.to(dev), a_var.to(dev), mask=mask.to(dev), **kw)
+    gg = torch.autograd.grad(got[0], lv)
+    rel = lambda p, q: float((p.detach().cpu().double() - q).norm() / q.norm().clamp_min(1e-30))
+    for p, q in zip(list(got) + list(gg), list(want) + list(gw)):
+        assert rel(p, q) < 1e-5, rel(p, q)
