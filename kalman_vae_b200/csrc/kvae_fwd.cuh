@@ -440,7 +440,11 @@ KV_FN void filter_sweep(const Args& a, const float* base, const FTiles<C>& tl, c
       project_obs<C>(g, Ct, muf, af);
       if (active && g.lane == 0) store_row<P>(a.a_filt + bt * P, af);
     }
+#ifdef KV_DIAG_NO_STORES   // diagnostic build only (tools/README.md): how long is the bare dependent chain without its outputs?
+    if (active && a.T < 0) {
+#else
     if (active) {
+#endif
       KV_UNROLL for (int r = 0; r < R; ++r) {
         store_row<N>(a.Sig_p + (bt * N + row0 + r) * N, Sp[r]);
         store_row<N>(a.Sig_f + (bt * N + row0 + r) * N, Sf[r]);
