@@ -30,6 +30,10 @@
 // csrc/kvae_seq_bwd.cuh).  The step arithmetic is the same code as the lane-group kernels (filter_step_math,
 // smoother_step_math, ... instantiated with L = 1: "publish" aliases registers).
 #pragma once
+#ifndef KV_SEQ_PF_L2
+#define KV_SEQ_PF_L2 6   // smoother: L2 prefetch distance (iterations beyond the two-ahead register loads); 0 = off
+#endif
+
 #include <cuda.h>
 #include "kvae_kernels.cuh"
 
@@ -422,6 +426,24 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 2) k_seq_fwd(Args a, Bas
       tma::load3d(tma::s32(buf), &mp.Sig_f, 0, t, b0, bar_st[slot].addr, pol_ef);
       tma::load3d(tma::s32(buf + TM::bytes), &mp.Sig_p, 0, t + 1, b0, bar_st[slot].addr, pol_ef);
     };
+    // ... and their lines are pulled into L2 KV_SEQ_PF_L2 iterations ahead (prefetch.global.L2, no registers): with the
+    // machine full an HBM round trip is longer than two smoother iterations, and the first use of a two-ahead register
+    // load was still 21 % of this kernel's stall samples (profiles/r02_ncu_hot_instructions_B262144_thread_per_sequence.txt)
+    const bool pf_on = T >= 64;   // (short sequences: the prologue costs more than the prefetch saves; T = 20: +2 %, T = 200: -4 %)
+    auto pf_l2 = [&](int t) {
+#if KV_SEQ_PF_L2 > 0
+      if (!pf_on) return;
+      const long bt = (long)bl * T + t;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mu_f + bt * N));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mu_p + (bt + 1) * N));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.alpha + (bt + 1) * K));
+#else
+      (void)t;
+#endif
+    };
+#if KV_SEQ_PF_L2 > 0
+    for (int t = T - 4; t > T - 4 - KV_SEQ_PF_L2 && t >= 0; --t) pf_l2(t);
+#endif
     if (T >= 2) load_vec(T - 2, pfA);
     if (T >= 3) load_vec(T - 3, pfB);
     if (tma::elect_one()) {
@@ -447,6 +469,9 @@ __global__ void __launch_bounds__(32 * KV_SEQ_MAXWARPS, 2) k_seq_fwd(Args a, Bas
         load_vec(t - 2, pf);
         if (tma::elect_one()) issue_st(t - 2, slot == 0 ? 2 : slot - 1);
       }
+#if KV_SEQ_PF_L2 > 0
+      if (t >= 2 + KV_SEQ_PF_L2) pf_l2(t - 2 - KV_SEQ_PF_L2);
+#endif
       bar_st[slot].wait();
       const float* sb = reinterpret_cast<const float*>(ring + slot * (2 * (int)TM::bytes));
       float Sf[R][N], Sp1[R][N];
