@@ -7,6 +7,10 @@
 // Equation labels (A.x) follow SURVEY.md Appendix A.  Tensor layouts are the reference's
 // batch-major [B,T,...] contiguous fp32 layouts (kalman_filter.py:193-201).
 #pragma once
+#ifndef KV_SMOOTH_PF_L2
+#define KV_SMOOTH_PF_L2 4   // lane-group smoother: L2 prefetch distance beyond the one-ahead register loads (0 = off)
+#endif
+
 #include "kvae_prims.cuh"
 
 namespace kvae {
@@ -583,6 +587,8 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     ins.commit(g);
     if (T >= 8) ins.prefetch(a, g, (long)b * T + (T - 8));
   }
+  const bool pf_l2 = T >= 64;   // (see k_seq_fwd: short sequences gain nothing)
+  (void)pf_l2;
   SmoothIn<C> pf;   // software prefetch: the states of the step after the current one
   if (T >= 2) load_smooth_in<C>(a, (long)b * T + (T - 2), row0, pf);
   for (int t = T - 2; t >= 0; --t) {
@@ -616,6 +622,19 @@ KV_FN void smoother_sweep(const Args& a, const float* base, const FTiles<C>& tl,
     //  mixing, so the first mixing FMA waited for the whole L2 round trip -- 40 % of this kernel's stall samples)
     if (staged && ((t + 1) & 3) == 0 && t + 1 >= 8) ins.prefetch(a, g, (long)b * T + (t + 1) - 8);
     if (t > 0) load_smooth_in<C>(a, bt - 1, row0, pf);
+#if defined(__CUDA_ARCH__) && KV_SMOOTH_PF_L2 > 0
+    if (pf_l2 && t > KV_SMOOTH_PF_L2) {   // long sequences: pull the rows of a later iteration into L2 (no registers held)
+      const long bq = bt - 1 - KV_SMOOTH_PF_L2;
+      KV_UNROLL for (int r = 0; r < R; ++r) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Sig_f + (bq * N + row0 + r) * N));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Sig_p + ((bq + 1) * N + row0 + r) * N));
+      }
+      if (g.lane == 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mu_f + bq * N));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mu_p + (bq + 1) * N));
+      }
+    }
+#endif
     ok = smoother_step_math<C>(g, tl, Sf, Sp1, muf, mup1, A1, Sig, mus) && ok;
     if (active) {
       KV_UNROLL for (int r = 0; r < R; ++r) store_row<N>(a.Sig_s + (bt * N + row0 + r) * N, Sig[r]);
